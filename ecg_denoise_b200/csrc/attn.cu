@@ -1,0 +1,422 @@
+// attn.cu -- attention half of the RA-LENet TransformerBlock, one CTA per ECG window.
+//
+//   y = x + proj( softmax(0.5 q k^T + rw_bias) v ),   [q | k | v] = LN1(x*sqrt(C) + P) [Wq ; Wkv]^T + b
+//
+// Reference: model/transformer.py:383-390 (forward_part1), :289-323 (MSAttention), :226-247
+// (LinearProjection), :179-181 (AbsPositionalEncoding), :534-558 (R-wave relative bias + mask_fill).
+//
+// A window is L tokens x C channels with L*C = 2048 (4096 for 512-sample windows), head_dim 4, so the
+// whole window (x, q, k, v) lives in shared memory and the L x L logits are never materialised:
+// each thread owns one (head, query) row and streams the keys with an online softmax.  The R-wave
+// bias is added from its (2W-1) x H table on the central W x W block only.
+#include "common.cuh"
+
+namespace {
+
+template <int C>
+size_t attn_fwd_smem(int L) { return sizeof(float) * ((size_t)L * lda_of<C>() + 3 * (size_t)L * C + SW_FLOATS + 128); }
+
+// ---------------------------------------------------------------------------------------------
+template <int C, int WIN>
+__global__ void __launch_bounds__(RL_NT) attn_fwd_kernel(const rl_attn_fwd_args a) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int LDA = lda_of<C>();
+  const int L = a.L, H = a.H, W = a.W, c0 = a.c0;
+  float* su = smem;
+  float* sq = su + L * LDA;
+  float* sk = sq + L * C;
+  float* sv = sk + L * C;
+  float* sw = sv + L * C;
+  float* stab = sw + SW_FLOATS;
+  const int tid = threadIdx.x;
+  const size_t woff = (size_t)blockIdx.x * L * C;
+  const float* xw = a.x + woff;
+
+  // 1. x*sqrt(C) + P -> LayerNorm -> su          (transformer.py:386-387)
+  if (a.flags & RL_F_PRENORM) {
+    const float sc = sqrtf((float)C);
+    const float* pe = a.pe;
+    const float* lw = a.ln_w;
+    const float* lb = a.ln_b;
+    ln_forward_rows<C>(
+        L, [&](int t, int c) { return fmaf(__ldg(xw + t * C + c), sc, __ldg(pe + t * C + c)); },
+        [&](int t, int c, float zh) { su[t * LDA + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c)); });
+  } else {
+    for (int i = tid; i < L * C; i += RL_NT) su[(i / C) * LDA + (i % C)] = __ldg(xw + i);
+  }
+  if (W > 0)
+    for (int i = tid; i < (2 * W - 1) * H; i += RL_NT) stab[i] = __ldg(a.table + i) * RL_LOG2E;
+  __syncthreads();
+
+  // 2. [q|k|v] = u [Wq;Wkv]^T + b   (N = 3C, K = C), weights streamed through sw in K chunks
+  {
+    TileAcc<4 * WIN, 6> acc;
+    acc.init(L, 3 * C);
+    const int ldd = 3 * C + 1;
+    const int KC = min(C, pow2_floor(SW_FLOATS / ldd));
+    for (int k0 = 0; k0 < C; k0 += KC) {
+      stage_wT(sw, ldd, a.wq, C, 0, C, k0, KC);
+      stage_wT(sw + C, ldd, a.wkv, C, 0, 2 * C, k0, KC);
+      __syncthreads();
+      acc.mac(su + k0, LDA, 1, sw, ldd, KC);
+      __syncthreads();
+    }
+    const float* bq = a.bq;
+    const float* bkv = a.bkv;
+    acc.epilogue([&](int t, int n, float v) {
+      if (n < C) {
+        sq[t * C + n] = v + (bq ? __ldg(bq + n) : 0.f);
+      } else {
+        v += bkv ? __ldg(bkv + n - C) : 0.f;
+        if (n < 2 * C) sk[t * C + n - C] = v; else sv[t * C + n - 2 * C] = v;
+      }
+    });
+  }
+  __syncthreads();
+  if (a.q) {
+    copy_s2g(a.q + woff, sq, L * C);
+    copy_s2g(a.k + woff, sk, L * C);
+    copy_s2g(a.v + woff, sv, L * C);
+  }
+
+  // 3. attention core: one (head, query) row per thread, online softmax in the log2 domain.
+  //    o overwrites q in place (only the owner thread ever reads q[i, 4h:4h+4]).
+  const float qs = 0.5f * RL_LOG2E;                  // head_dim^-0.5 (transformer.py:278) * log2(e)
+  for (int item = tid; item < H * L; item += RL_NT) {
+    const int i = item % L, h = item / L;
+    float4 q4 = *reinterpret_cast<const float4*>(sq + i * C + 4 * h);
+    q4.x *= qs; q4.y *= qs; q4.z *= qs; q4.w *= qs;
+    const bool central = (W > 0) && ((unsigned)(i - c0) < (unsigned)W);
+    float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    const float* kp = sk + 4 * h;
+    const float* vp = sv + 4 * h;
+    for (int j0 = 0; j0 < L; j0 += 8) {
+      float s[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float4 k4 = *reinterpret_cast<const float4*>(kp + (j0 + jj) * C);
+        s[jj] = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
+      }
+      if (central) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = j0 + jj;
+          if ((unsigned)(j - c0) < (unsigned)W) s[jj] += stab[(i - j + W - 1) * H + h];
+        }
+      }
+      float cm = s[0];
+#pragma unroll
+      for (int jj = 1; jj < 8; ++jj) cm = fmaxf(cm, s[jj]);
+      const float mn = fmaxf(m, cm);
+      const float corr = exp2f(m - mn);
+      l *= corr; o0 *= corr; o1 *= corr; o2 *= corr; o3 *= corr;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float p = exp2f(s[jj] - mn);
+        const float4 v4 = *reinterpret_cast<const float4*>(vp + (j0 + jj) * C);
+        l += p;
+        o0 = fmaf(p, v4.x, o0); o1 = fmaf(p, v4.y, o1); o2 = fmaf(p, v4.z, o2); o3 = fmaf(p, v4.w, o3);
+      }
+      m = mn;
+    }
+    const float inv = 1.0f / l;
+    *reinterpret_cast<float4*>(sq + i * C + 4 * h) = make_float4(o0 * inv, o1 * inv, o2 * inv, o3 * inv);
+    if (a.lse) a.lse[(size_t)blockIdx.x * H * L + item] = m + log2f(l);
+  }
+  __syncthreads();
+  if (a.o) copy_s2g(a.o + woff, sq, L * C);
+
+  // 4. y = x + o Wp^T + bp        (transformer.py:320, :405)
+  {
+    TileAcc<4 * WIN, 2> acc;
+    acc.init(L, C);
+    const int ldd = C + 1;
+    const int KC = min(C, pow2_floor(SW_FLOATS / ldd));
+    for (int k0 = 0; k0 < C; k0 += KC) {
+      stage_wT(sw, ldd, a.wp, C, 0, C, k0, KC);
+      __syncthreads();
+      acc.mac(sq + k0, C, 1, sw, ldd, KC);
+      __syncthreads();
+    }
+    const float* bp = a.bp;
+    float* yw = a.y + woff;
+    const bool resid = a.flags & RL_F_RESIDUAL;
+    acc.epilogue([&](int t, int n, float v) {
+      v += bp ? __ldg(bp + n) : 0.f;
+      if (resid) v += __ldg(xw + t * C + n);
+      yw[t * C + n] = v;
+    });
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int C>
+size_t attn_bwd_smem(int L) {
+  return sizeof(float) * (7 * (size_t)L * C + 2 * ((size_t)L * C / 4) + (size_t)L * lda_of<C>() + SW_FLOATS + 256 +
+                          2 * C);
+}
+
+template <int C, int WIN>
+__global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args a) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int LDA = lda_of<C>();
+  const int L = a.L, H = a.H, W = a.W, c0 = a.c0;
+  const int LC = L * C;
+  float* sq = smem;
+  float* sk = sq + LC;
+  float* sv = sk + LC;
+  float* sdo = sv + LC;
+  float* sdq = sdo + LC;
+  float* sdk = sdq + LC;
+  float* sdv = sdk + LC;
+  float* sD = sdv + LC;
+  float* sLse = sD + LC / 4;
+  float* su = sLse + LC / 4;
+  float* sw = su + L * LDA;
+  float* stab = sw + SW_FLOATS;
+  float* stabg = stab + 128;
+  float* s_gb = stabg + 128;
+  const int tid = threadIdx.x;
+  const size_t woff = (size_t)blockIdx.x * LC;
+  const float* gw = a.g + woff;
+  const float* xw = a.x + woff;
+
+  // 1. stage saved tensors; g -> sdq (temp), o -> sdk (temp)
+  copy_g2s(sq, a.q + woff, LC);
+  copy_g2s(sk, a.k + woff, LC);
+  copy_g2s(sv, a.v + woff, LC);
+  copy_g2s(sdq, gw, LC);
+  copy_g2s(sdk, a.o + woff, LC);
+  copy_g2s(sLse, a.lse + (size_t)blockIdx.x * (LC / 4), LC / 4);
+  if (tid < 128) {
+    stabg[tid] = 0.f;
+    stab[tid] = (W > 0 && tid < (2 * W - 1) * H) ? __ldg(a.table + tid) * RL_LOG2E : 0.f;
+  }
+  for (int i = tid; i < 2 * C; i += RL_NT) s_gb[i] = 0.f;
+  __syncthreads();
+
+  // 2. do = g Wp            (dgrad of proj; B(k,n) = Wp[k][n] natural layout)
+  {
+    TileAcc<4 * WIN, 2> acc;
+    acc.init(L, C);
+    const int ldd = C + 1;
+    const int KC = min(C, pow2_floor(SW_FLOATS / ldd));
+    for (int k0 = 0; k0 < C; k0 += KC) {
+      stage_w(sw, ldd, a.wp, C, k0, KC, 0, C);
+      __syncthreads();
+      acc.mac(sdq + k0, C, 1, sw, ldd, KC);
+      __syncthreads();
+    }
+    acc.epilogue([&](int t, int n, float v) { sdo[t * C + n] = v; });
+  }
+  __syncthreads();
+  // 3. D[h,i] = do_i . o_i
+  for (int item = tid; item < H * L; item += RL_NT) {
+    const int i = item % L, h = item / L;
+    const float4 d4 = *reinterpret_cast<const float4*>(sdo + i * C + 4 * h);
+    const float4 o4 = *reinterpret_cast<const float4*>(sdk + i * C + 4 * h);
+    sD[item] = d4.x * o4.x + d4.y * o4.y + d4.z * o4.z + d4.w * o4.w;
+  }
+  __syncthreads();
+
+  const float qs = 0.5f * RL_LOG2E;
+  // 4a. dq: one (head, query) row per thread
+  for (int item = tid; item < H * L; item += RL_NT) {
+    const int i = item % L, h = item / L;
+    float4 q4 = *reinterpret_cast<const float4*>(sq + i * C + 4 * h);
+    q4.x *= qs; q4.y *= qs; q4.z *= qs; q4.w *= qs;
+    const float4 d4 = *reinterpret_cast<const float4*>(sdo + i * C + 4 * h);
+    const float Di = sD[item], lse = sLse[item];
+    const bool central = (W > 0) && ((unsigned)(i - c0) < (unsigned)W);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float* kp = sk + 4 * h;
+    const float* vp = sv + 4 * h;
+    for (int j = 0; j < L; ++j) {
+      const float4 k4 = *reinterpret_cast<const float4*>(kp + j * C);
+      const float4 v4 = *reinterpret_cast<const float4*>(vp + j * C);
+      float s = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
+      const bool cpair = central && ((unsigned)(j - c0) < (unsigned)W);
+      if (cpair) s += stab[(i - j + W - 1) * H + h];
+      const float p = exp2f(s - lse);
+      const float dp = d4.x * v4.x + d4.y * v4.y + d4.z * v4.z + d4.w * v4.w;
+      const float ds = p * (dp - Di);
+      a0 = fmaf(ds, k4.x, a0); a1 = fmaf(ds, k4.y, a1); a2 = fmaf(ds, k4.z, a2); a3 = fmaf(ds, k4.w, a3);
+      if (cpair && a.d_table) atomicAdd(&stabg[(i - j + W - 1) * H + h], ds);
+    }
+    *reinterpret_cast<float4*>(sdq + i * C + 4 * h) = make_float4(0.5f * a0, 0.5f * a1, 0.5f * a2, 0.5f * a3);
+  }
+  // 4b. dk, dv: one (head, key) column per thread  (sdq is not read here, sdk/sdv are only written)
+  __syncthreads();   // sdk (o) was read in step 3 by other threads; step 4a done with sdq writes
+  for (int item = tid; item < H * L; item += RL_NT) {
+    const int j = item % L, h = item / L;
+    const float4 k4 = *reinterpret_cast<const float4*>(sk + j * C + 4 * h);
+    const float4 v4 = *reinterpret_cast<const float4*>(sv + j * C + 4 * h);
+    const bool centralj = (W > 0) && ((unsigned)(j - c0) < (unsigned)W);
+    float k0a = 0.f, k1a = 0.f, k2a = 0.f, k3a = 0.f, v0a = 0.f, v1a = 0.f, v2a = 0.f, v3a = 0.f;
+    const float* qp = sq + 4 * h;
+    const float* dp_ = sdo + 4 * h;
+    const float* Dp = sD + h * L;
+    const float* Lp = sLse + h * L;
+    for (int i = 0; i < L; ++i) {
+      const float4 q4 = *reinterpret_cast<const float4*>(qp + i * C);
+      const float4 d4 = *reinterpret_cast<const float4*>(dp_ + i * C);
+      float s = qs * (q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w);
+      if (centralj && ((unsigned)(i - c0) < (unsigned)W)) s += stab[(i - j + W - 1) * H + h];
+      const float p = exp2f(s - Lp[i]);
+      v0a = fmaf(p, d4.x, v0a); v1a = fmaf(p, d4.y, v1a); v2a = fmaf(p, d4.z, v2a); v3a = fmaf(p, d4.w, v3a);
+      const float dpv = d4.x * v4.x + d4.y * v4.y + d4.z * v4.z + d4.w * v4.w;
+      const float ds = p * (dpv - Dp[i]);
+      k0a = fmaf(ds, q4.x, k0a); k1a = fmaf(ds, q4.y, k1a); k2a = fmaf(ds, q4.z, k2a); k3a = fmaf(ds, q4.w, k3a);
+    }
+    *reinterpret_cast<float4*>(sdk + j * C + 4 * h) = make_float4(0.5f * k0a, 0.5f * k1a, 0.5f * k2a, 0.5f * k3a);
+    *reinterpret_cast<float4*>(sdv + j * C + 4 * h) = make_float4(v0a, v1a, v2a, v3a);
+  }
+  __syncthreads();
+
+  // 5. dqkv scratch [t][dq | dk | dv] for the weight-gradient GEMMs
+  {
+    float* dst = a.dqkv + (size_t)blockIdx.x * 3 * LC;
+    constexpr int C4 = C / 4;
+    for (int i = tid; i < 3 * L * C4; i += RL_NT) {
+      const int c4 = i % C4, seg = (i / C4) % 3, t = i / (3 * C4);
+      const float* src = (seg == 0) ? sdq : (seg == 1) ? sdk : sdv;
+      reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src + t * C)[c4];
+    }
+  }
+
+  // 6. du = dq Wq + dk Wk + dv Wv       (K = 3C in three segments)
+  {
+    TileAcc<4 * WIN, 2> acc;
+    acc.init(L, C);
+    const int ldd = C + 1;
+    const int KC = min(C, pow2_floor(SW_FLOATS / ldd));
+    for (int seg = 0; seg < 3; ++seg) {
+      const float* As = (seg == 0) ? sdq : (seg == 1) ? sdk : sdv;
+      const float* Wsrc = (seg == 0) ? a.wq : (seg == 1) ? a.wkv : a.wkv + (size_t)C * C;
+      for (int k0 = 0; k0 < C; k0 += KC) {
+        stage_w(sw, ldd, Wsrc, C, k0, KC, 0, C);
+        __syncthreads();
+        acc.mac(As + k0, C, 1, sw, ldd, KC);
+        __syncthreads();
+      }
+    }
+    acc.epilogue([&](int t, int n, float v) { su[t * LDA + n] = v; });
+  }
+  __syncthreads();
+
+  // 7. LayerNorm backward, positional scale, residual
+  float* dxw = a.dx + woff;
+  float* uw = a.u + woff;
+  const bool resid = a.flags & RL_F_RESIDUAL;
+  if (a.flags & RL_F_PRENORM) {
+    const float sc = sqrtf((float)C);
+    const float* pe = a.pe;
+    const float* lw = a.ln_w;
+    const float* lb = a.ln_b;
+    ln_backward_rows<C>(
+        L, lw, s_gb, [&](int t, int c) { return fmaf(__ldg(xw + t * C + c), sc, __ldg(pe + t * C + c)); },
+        [&](int t, int c) { return su[t * LDA + c]; },
+        [&](int t, int c, float dz, float zh) {
+          dxw[t * C + c] = (resid ? __ldg(gw + t * C + c) : 0.f) + sc * dz;
+          uw[t * C + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c));
+        });
+    __syncthreads();
+    if (a.d_ln_w)
+      for (int i = tid; i < C; i += RL_NT) {
+        atomicAdd(a.d_ln_w + i, s_gb[i]);
+        atomicAdd(a.d_ln_b + i, s_gb[C + i]);
+      }
+  } else {
+    for (int i = tid; i < LC; i += RL_NT) {
+      const int t = i / C, c = i % C;
+      dxw[i] = su[t * LDA + c] + (resid ? __ldg(gw + i) : 0.f);
+      uw[i] = __ldg(xw + i);
+    }
+  }
+  if (a.d_table && W > 0)
+    for (int i = tid; i < (2 * W - 1) * H; i += RL_NT) atomicAdd(a.d_table + i, stabg[i]);
+}
+
+template <int C>
+int launch_fwd(const rl_attn_fwd_args* a, cudaStream_t st) {
+  const int win = a->L * C / 2048;
+  const size_t smem = attn_fwd_smem<C>(a->L);
+  if (win == 1) {
+    if (int rc = rl_set_smem(attn_fwd_kernel<C, 1>, smem)) return rc;
+    attn_fwd_kernel<C, 1><<<a->B, RL_NT, smem, st>>>(*a);
+  } else {
+    if (int rc = rl_set_smem(attn_fwd_kernel<C, 2>, smem)) return rc;
+    attn_fwd_kernel<C, 2><<<a->B, RL_NT, smem, st>>>(*a);
+  }
+  return rl_check_launch("attn_fwd_kernel");
+}
+
+template <int C>
+int launch_bwd(const rl_attn_bwd_args* a, cudaStream_t st) {
+  const int win = a->L * C / 2048;
+  const size_t smem = attn_bwd_smem<C>(a->L);
+  if (win == 1) {
+    if (int rc = rl_set_smem(attn_bwd_kernel<C, 1>, smem)) return rc;
+    attn_bwd_kernel<C, 1><<<a->B, RL_NT, smem, st>>>(*a);
+  } else {
+    if (int rc = rl_set_smem(attn_bwd_kernel<C, 2>, smem)) return rc;
+    attn_bwd_kernel<C, 2><<<a->B, RL_NT, smem, st>>>(*a);
+  }
+  return rl_check_launch("attn_bwd_kernel");
+}
+
+int check_shape(int B, int L, int C, int H, int W, int c0) {
+  RL_REQUIRE(B > 0, RL_ERR_SHAPE, "attn: B=%d", B);
+  RL_REQUIRE(C == 8 || C == 16 || C == 32 || C == 64 || C == 128, RL_ERR_SHAPE, "attn: unsupported C=%d", C);
+  RL_REQUIRE(H * RL_HD == C, RL_ERR_SHAPE, "attn: head_dim must be 4 (C=%d, H=%d)", C, H);
+  RL_REQUIRE(L * C == 2048 || L * C == 4096, RL_ERR_SHAPE, "attn: L*C must be 2048 or 4096 (L=%d, C=%d)", L, C);
+  RL_REQUIRE(W >= 0 && (W == 0 || (c0 >= 0 && c0 + W <= L && (2 * W - 1) * H <= 128)), RL_ERR_SHAPE,
+             "attn: bad R-wave window W=%d c0=%d L=%d H=%d", W, c0, L, H);
+  return RL_OK;
+}
+
+}  // namespace
+
+extern "C" int ralenet_attn_fwd(const rl_attn_fwd_args* a, void* stream) {
+  RL_REQUIRE(a, RL_ERR_NULL, "attn_fwd: args is NULL");
+  if (int rc = check_shape(a->B, a->L, a->C, a->H, a->W, a->c0)) return rc;
+  RL_REQUIRE(a->x && a->y && a->wq && a->wkv && a->wp, RL_ERR_NULL, "attn_fwd: NULL tensor");
+  RL_REQUIRE(!(a->flags & RL_F_PRENORM) || (a->pe && a->ln_w && a->ln_b), RL_ERR_NULL, "attn_fwd: prenorm needs pe/ln");
+  RL_REQUIRE(a->W == 0 || a->table, RL_ERR_NULL, "attn_fwd: W>0 needs table");
+  RL_REQUIRE(!a->q || (a->k && a->v && a->o && a->lse), RL_ERR_NULL, "attn_fwd: partial save set");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a->C) {
+    case 8: return launch_fwd<8>(a, st);
+    case 16: return launch_fwd<16>(a, st);
+    case 32: return launch_fwd<32>(a, st);
+    case 64: return launch_fwd<64>(a, st);
+    case 128: return launch_fwd<128>(a, st);
+  }
+  return RL_ERR_SHAPE;
+}
+
+extern "C" int ralenet_attn_bwd(const rl_attn_bwd_args* a, void* stream) {
+  RL_REQUIRE(a, RL_ERR_NULL, "attn_bwd: args is NULL");
+  if (int rc = check_shape(a->B, a->L, a->C, a->H, a->W, a->c0)) return rc;
+  RL_REQUIRE(a->g && a->x && a->wq && a->wkv && a->wp && a->q && a->k && a->v && a->o && a->lse && a->dx && a->dqkv &&
+                 a->u,
+             RL_ERR_NULL, "attn_bwd: NULL tensor");
+  RL_REQUIRE(!(a->flags & RL_F_PRENORM) || (a->pe && a->ln_w && a->ln_b), RL_ERR_NULL, "attn_bwd: prenorm needs pe/ln");
+  RL_REQUIRE(a->W == 0 || a->table, RL_ERR_NULL, "attn_bwd: W>0 needs table");
+  RL_REQUIRE(!a->d_ln_w == !a->d_ln_b, RL_ERR_NULL, "attn_bwd: d_ln_w/d_ln_b must be both set or both NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = RL_ERR_SHAPE;
+  switch (a->C) {
+    case 8: rc = launch_bwd<8>(a, st); break;
+    case 16: rc = launch_bwd<16>(a, st); break;
+    case 32: rc = launch_bwd<32>(a, st); break;
+    case 64: rc = launch_bwd<64>(a, st); break;
+    case 128: rc = launch_bwd<128>(a, st); break;
+  }
+  if (rc) return rc;
+  const int M = a->B * a->L, C = a->C;
+  if ((rc = rl_launch_wgrad(a->g, C, a->o, C, M, C, C, a->d_wp, a->d_bp, st))) return rc;
+  if ((rc = rl_launch_wgrad(a->dqkv, 3 * C, a->u, C, M, C, C, a->d_wq, a->d_bq, st))) return rc;
+  if ((rc = rl_launch_wgrad(a->dqkv + C, 3 * C, a->u, C, M, 2 * C, C, a->d_wkv, a->d_bkv, st))) return rc;
+  return RL_OK;
+}

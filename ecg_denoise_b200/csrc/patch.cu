@@ -1,0 +1,190 @@
+// patch.cu -- PatchMerging / PatchSeparate of the RA-LENet U-shape, one CTA per window.
+//
+//   merge    (model/transformer.py:440-460): cat(x[:,0::2], x[:,1::2], -1) -> LN(2C) -> Linear(2C,2C,no bias)
+//            the even/odd concat is exactly x viewed as [L/2][2C], so no gather is needed.
+//   separate (model/transformer.py:418-424): 'b l (c1 c2) -> b (c1 l) c2' -> LN(C/2) -> Linear(C/2,C/2,no bias)
+//            rows 0..L-1 take channels [0,C/2), rows L..2L-1 take [C/2,C); + U-skip (:650,654,658).
+// Both are "rows x Cn" LayerNorm + square GEMM with rows*Cn = L*C; templated on Cn.
+#include "common.cuh"
+
+namespace {
+
+// element (r, c) of the re-laid-out input inside one window
+__device__ __forceinline__ int src_index(int mode, int L, int C, int Cn, int r, int c) {
+  if (mode == 0) return r * Cn + c;                         // merge: contiguous view
+  return (r < L) ? r * C + c : (r - L) * C + Cn + c;        // separate
+}
+
+template <int CN>
+size_t patch_smem(int rows) { return sizeof(float) * (2 * (size_t)rows * lda_of<CN>() + SW_FLOATS + 2 * CN + 64); }
+
+template <int CN, int WIN>
+__global__ void __launch_bounds__(RL_NT) patch_fwd_kernel(const rl_patch_fwd_args a) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int LDA = lda_of<CN>();
+  const int L = a.L, C = a.C, mode = a.mode;
+  const int rows = L * C / CN;
+  float* su = smem;
+  float* sw = su + 2 * rows * LDA;
+  const size_t woff = (size_t)blockIdx.x * L * C;
+  const float* xw = a.x + woff;
+  {
+    const float* lw = a.ln_w;
+    const float* lb = a.ln_b;
+    float* us = a.u ? a.u + woff : nullptr;
+    ln_forward_rows<CN>(
+        rows, [&](int r, int c) { return __ldg(xw + src_index(mode, L, C, CN, r, c)); },
+        [&](int r, int c, float zh) {
+          const float u = fmaf(zh, __ldg(lw + c), __ldg(lb + c));
+          su[r * LDA + c] = u;
+          if (us) us[r * CN + c] = u;
+        });
+  }
+  __syncthreads();
+  TileAcc<4 * WIN, 2> acc;
+  acc.init(rows, CN);
+  const int ldd = CN + 1;
+  const int KC = min(CN, pow2_floor(SW_FLOATS / ldd));
+  for (int k0 = 0; k0 < CN; k0 += KC) {
+    stage_wT(sw, ldd, a.w, CN, 0, CN, k0, KC);
+    __syncthreads();
+    acc.mac(su + k0, LDA, 1, sw, ldd, KC);
+    __syncthreads();
+  }
+  const float* sk = a.skip ? a.skip + woff : nullptr;
+  float* yw = a.y + woff;
+  acc.epilogue([&](int r, int n, float v) {
+    if (sk) v += __ldg(sk + r * CN + n);
+    yw[r * CN + n] = v;
+  });
+}
+
+template <int CN, int WIN>
+__global__ void __launch_bounds__(RL_NT) patch_bwd_kernel(const rl_patch_bwd_args a, float* __restrict__ gsum) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int LDA = lda_of<CN>();
+  const int L = a.L, C = a.C, mode = a.mode;
+  const int rows = L * C / CN;
+  float* sg = smem;
+  float* su = sg + rows * LDA;
+  float* sw = su + rows * LDA;
+  float* s_gb = sw + SW_FLOATS;
+  const int tid = threadIdx.x;
+  const size_t woff = (size_t)blockIdx.x * L * C;
+  const float* gw = a.g + woff;
+  const float* g2w = a.g2 ? a.g2 + woff : nullptr;
+  const float* xw = a.x + woff;
+  for (int i = tid; i < rows * CN; i += RL_NT) {
+    float v = __ldg(gw + i);
+    if (g2w) {
+      v += __ldg(g2w + i);
+      gsum[woff + i] = v;
+    }
+    sg[(i / CN) * LDA + (i % CN)] = v;
+  }
+  for (int i = tid; i < 2 * CN; i += RL_NT) s_gb[i] = 0.f;
+  __syncthreads();
+  {
+    TileAcc<4 * WIN, 2> acc;
+    acc.init(rows, CN);
+    const int ldd = CN + 1;
+    const int KC = min(CN, pow2_floor(SW_FLOATS / ldd));
+    for (int k0 = 0; k0 < CN; k0 += KC) {
+      stage_w(sw, ldd, a.w, CN, k0, KC, 0, CN);
+      __syncthreads();
+      acc.mac(sg + k0, LDA, 1, sw, ldd, KC);
+      __syncthreads();
+    }
+    acc.epilogue([&](int r, int n, float v) { su[r * LDA + n] = v; });
+  }
+  __syncthreads();
+  float* dxw = a.dx + woff;
+  ln_backward_rows<CN>(
+      rows, a.ln_w, s_gb, [&](int r, int c) { return __ldg(xw + src_index(mode, L, C, CN, r, c)); },
+      [&](int r, int c) { return su[r * LDA + c]; },
+      [&](int r, int c, float dz, float) { dxw[src_index(mode, L, C, CN, r, c)] = dz; });
+  __syncthreads();
+  if (a.d_ln_w)
+    for (int i = tid; i < CN; i += RL_NT) {
+      atomicAdd(a.d_ln_w + i, s_gb[i]);
+      atomicAdd(a.d_ln_b + i, s_gb[CN + i]);
+    }
+}
+
+template <int CN>
+int launch_fwd(const rl_patch_fwd_args* a, cudaStream_t st) {
+  const int rows = a->L * a->C / CN;
+  const size_t smem = patch_smem<CN>(rows);
+  if (a->L * a->C == 2048) {
+    if (int rc = rl_set_smem(patch_fwd_kernel<CN, 1>, smem)) return rc;
+    patch_fwd_kernel<CN, 1><<<a->B, RL_NT, smem, st>>>(*a);
+  } else {
+    if (int rc = rl_set_smem(patch_fwd_kernel<CN, 2>, smem)) return rc;
+    patch_fwd_kernel<CN, 2><<<a->B, RL_NT, smem, st>>>(*a);
+  }
+  return rl_check_launch("patch_fwd_kernel");
+}
+
+template <int CN>
+int launch_bwd(const rl_patch_bwd_args* a, float* gsum, cudaStream_t st) {
+  const int rows = a->L * a->C / CN;
+  const size_t smem = patch_smem<CN>(rows);
+  if (a->L * a->C == 2048) {
+    if (int rc = rl_set_smem(patch_bwd_kernel<CN, 1>, smem)) return rc;
+    patch_bwd_kernel<CN, 1><<<a->B, RL_NT, smem, st>>>(*a, gsum);
+  } else {
+    if (int rc = rl_set_smem(patch_bwd_kernel<CN, 2>, smem)) return rc;
+    patch_bwd_kernel<CN, 2><<<a->B, RL_NT, smem, st>>>(*a, gsum);
+  }
+  return rl_check_launch("patch_bwd_kernel");
+}
+
+int check_shape(int B, int L, int C, int mode, int* cn) {
+  RL_REQUIRE(B > 0 && (mode == 0 || mode == 1), RL_ERR_SHAPE, "patch: B=%d mode=%d", B, mode);
+  RL_REQUIRE(L * C == 2048 || L * C == 4096, RL_ERR_SHAPE, "patch: L*C must be 2048 or 4096 (L=%d, C=%d)", L, C);
+  const int CN = mode == 0 ? 2 * C : C / 2;
+  RL_REQUIRE(CN == 8 || CN == 16 || CN == 32 || CN == 64 || CN == 128, RL_ERR_SHAPE, "patch: unsupported width %d", CN);
+  RL_REQUIRE(mode == 1 || L % 2 == 0, RL_ERR_SHAPE, "patch: odd L=%d", L);
+  *cn = CN;
+  return RL_OK;
+}
+
+}  // namespace
+
+extern "C" int ralenet_patch_fwd(const rl_patch_fwd_args* a, void* stream) {
+  RL_REQUIRE(a, RL_ERR_NULL, "patch_fwd: args is NULL");
+  int CN = 0;
+  if (int rc = check_shape(a->B, a->L, a->C, a->mode, &CN)) return rc;
+  RL_REQUIRE(a->x && a->y && a->w && a->ln_w && a->ln_b, RL_ERR_NULL, "patch_fwd: NULL tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (CN) {
+    case 8: return launch_fwd<8>(a, st);
+    case 16: return launch_fwd<16>(a, st);
+    case 32: return launch_fwd<32>(a, st);
+    case 64: return launch_fwd<64>(a, st);
+    case 128: return launch_fwd<128>(a, st);
+  }
+  return RL_ERR_SHAPE;
+}
+
+// gsum: scratch [B, L*C] holding g + g2 when g2 is given (dx is used for it: see below)
+extern "C" int ralenet_patch_bwd(const rl_patch_bwd_args* a, void* stream) {
+  RL_REQUIRE(a, RL_ERR_NULL, "patch_bwd: args is NULL");
+  int CN = 0;
+  if (int rc = check_shape(a->B, a->L, a->C, a->mode, &CN)) return rc;
+  RL_REQUIRE(a->g && a->x && a->w && a->ln_w && a->u && a->dx, RL_ERR_NULL, "patch_bwd: NULL tensor");
+  RL_REQUIRE(!a->d_ln_w == !a->d_ln_b, RL_ERR_NULL, "patch_bwd: d_ln_w/d_ln_b must be both set or both NULL");
+  RL_REQUIRE(!a->g2 || a->gsum, RL_ERR_NULL, "patch_bwd: g2 needs the gsum scratch");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = RL_ERR_SHAPE;
+  switch (CN) {
+    case 8: rc = launch_bwd<8>(a, a->gsum, st); break;
+    case 16: rc = launch_bwd<16>(a, a->gsum, st); break;
+    case 32: rc = launch_bwd<32>(a, a->gsum, st); break;
+    case 64: rc = launch_bwd<64>(a, a->gsum, st); break;
+    case 128: rc = launch_bwd<128>(a, a->gsum, st); break;
+  }
+  if (rc) return rc;
+  const int M = a->B * (a->L * a->C / CN);
+  return rl_launch_wgrad(a->g2 ? a->gsum : a->g, CN, a->u, CN, M, CN, CN, a->d_w, nullptr, st);
+}

@@ -1,0 +1,307 @@
+"""GPU parity, per kernel: every C entry point (called through the ctypes ABI via the autograd Functions)
+against the CPU oracle in float64 on the same seeded inputs.
+
+Tolerance: |d| <= rtol * (|ref| + rms(ref)), rtol = 1e-3 for the fp32 path.
+The measured error is written to gpurun_out/parity_ops.json for the record.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ralenet_oracle as O
+from tests.common import rel_rms_err
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-3
+REPORT = {}
+
+
+def _record(name, err):
+    REPORT[name] = float(err)
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/parity_ops.json", "w") as f:
+            json.dump(REPORT, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def _cmp(name, got: torch.Tensor, ref: torch.Tensor, rtol=RTOL):
+    assert tuple(got.shape) == tuple(ref.shape), (name, got.shape, ref.shape)
+    err = rel_rms_err(got.detach().double().cpu().numpy(), ref.detach().double().cpu().numpy())
+    _record(name, err)
+    assert math.isfinite(err) and err <= rtol, f"{name}: rel err {err:.3e} > {rtol}"
+
+
+def _rand(rs, *shape, scale=1.0):
+    return torch.from_numpy(rs.standard_normal(shape) * scale)
+
+
+def _block_params(rs, C, le):
+    p = {
+        "norm1.weight": 1 + 0.1 * _rand(rs, C), "norm1.bias": 0.1 * _rand(rs, C),
+        "attn.qkv_proj.to_q.weight": _rand(rs, C, C, scale=C ** -0.5), "attn.qkv_proj.to_q.bias": 0.1 * _rand(rs, C),
+        "attn.qkv_proj.to_kv.weight": _rand(rs, 2 * C, C, scale=C ** -0.5),
+        "attn.qkv_proj.to_kv.bias": 0.1 * _rand(rs, 2 * C),
+        "attn.proj.weight": _rand(rs, C, C, scale=C ** -0.5), "attn.proj.bias": 0.1 * _rand(rs, C),
+        "norm2.weight": 1 + 0.1 * _rand(rs, C), "norm2.bias": 0.1 * _rand(rs, C),
+        "mlp.fc1.weight": _rand(rs, 4 * C, C, scale=C ** -0.5), "mlp.fc1.bias": 0.1 * _rand(rs, 4 * C),
+        "mlp.fc2.weight": _rand(rs, C, 4 * C, scale=(4 * C) ** -0.5), "mlp.fc2.bias": 0.1 * _rand(rs, C),
+    }
+    if le == 1:
+        p["mlp.leconv.partial_conv3.weight"] = _rand(rs, 1, 1, 3, scale=0.5)
+    elif le == 2:
+        p["mlp.leconv.weight"] = _rand(rs, 4 * C, 1, 3, scale=0.5)
+    return p
+
+
+def _dev(t, grad=True):
+    return t.float().cuda().requires_grad_(grad)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ecg_denoise_b200 import ops as _ops
+    return _ops
+
+
+@pytest.mark.parametrize("stage", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("bias", [True, False])
+def test_attn_block(ops, stage, bias):
+    if bias and stage == 4:
+        pytest.skip("no R-wave table at stage 4")
+    rs = np.random.RandomState(100 + stage)
+    C, H, L = O.CHANNELS[stage], O.HEADS[stage], O.LENGTHS[stage]
+    B = 3
+    p = _block_params(rs, C, 0)
+    W = O.RW_WINDOW[stage] if bias else 0
+    table = 0.5 * _rand(rs, 2 * W - 1, H) if bias else None
+    x = _rand(rs, B, L, C)
+    g = _rand(rs, B, L, C)
+    y_ref, saved = O.attn_block_fwd(x, p, H, table, W)
+    dx_ref, gr = O.attn_block_bwd(g, saved, p, H, table, W)
+
+    d = {k: _dev(v) for k, v in p.items()}
+    xt, tt = _dev(x), (_dev(table) if bias else None)
+    y = ops.AttnBlockFn.apply(xt, d["norm1.weight"], d["norm1.bias"], d["attn.qkv_proj.to_q.weight"],
+                              d["attn.qkv_proj.to_q.bias"], d["attn.qkv_proj.to_kv.weight"],
+                              d["attn.qkv_proj.to_kv.bias"], d["attn.proj.weight"], d["attn.proj.bias"], tt, H, W,
+                              (L - W) // 2 if bias else 0, ops.RL_F_PRENORM | ops.RL_F_RESIDUAL)
+    tag = f"attn/s{stage}/{'rw' if bias else 'plain'}"
+    _cmp(tag + "/y", y, y_ref)
+    y.backward(g.float().cuda())
+    _cmp(tag + "/dx", xt.grad, dx_ref)
+    for k in ("norm1.weight", "norm1.bias", "attn.qkv_proj.to_q.weight", "attn.qkv_proj.to_q.bias",
+              "attn.qkv_proj.to_kv.weight", "attn.qkv_proj.to_kv.bias", "attn.proj.weight", "attn.proj.bias"):
+        _cmp(f"{tag}/d_{k}", d[k].grad, gr[k])
+    if bias:
+        _cmp(tag + "/d_table", tt.grad, gr["table"])
+
+
+def test_attn_plain_msattention(ops):
+    """MSAttention.forward alone: no pre-norm, no residual (flags = 0)."""
+    rs = np.random.RandomState(7)
+    C, H, L, B = 16, 4, 128, 2
+    p = _block_params(rs, C, 0)
+    x = _rand(rs, B, L, C)
+    u = x
+    q = u @ p["attn.qkv_proj.to_q.weight"].t() + p["attn.qkv_proj.to_q.bias"]
+    kv = u @ p["attn.qkv_proj.to_kv.weight"].t() + p["attn.qkv_proj.to_kv.bias"]
+    qh, kh, vh = (t.reshape(B, L, H, 4).permute(0, 2, 1, 3) for t in (q, kv[..., :C], kv[..., C:]))
+    o = (torch.softmax(0.5 * qh @ kh.transpose(-1, -2), -1) @ vh).permute(0, 2, 1, 3).reshape(B, L, C)
+    ref = o @ p["attn.proj.weight"].t() + p["attn.proj.bias"]
+    d = {k: _dev(v, False) for k, v in p.items()}
+    y = ops.AttnBlockFn.apply(_dev(x, False), None, None, d["attn.qkv_proj.to_q.weight"], d["attn.qkv_proj.to_q.bias"],
+                              d["attn.qkv_proj.to_kv.weight"], d["attn.qkv_proj.to_kv.bias"], d["attn.proj.weight"],
+                              d["attn.proj.bias"], None, H, 0, 0, 0)
+    _cmp("attn/msattention_only/y", y, ref)
+
+
+@pytest.mark.parametrize("stage", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("le", [0, 1, 2])
+def test_ffn_block(ops, stage, le):
+    rs = np.random.RandomState(200 + stage * 3 + le)
+    C, L = O.CHANNELS[stage], O.LENGTHS[stage]
+    B = 3
+    p = _block_params(rs, C, le)
+    x = _rand(rs, B, L, C)
+    g = _rand(rs, B, L, C)
+    y_ref, saved = O.ffn_block_fwd(x, p)
+    dx_ref, gr = O.ffn_block_bwd(g, saved, p)
+    d = {k: _dev(v) for k, v in p.items()}
+    lew = d.get("mlp.leconv.partial_conv3.weight", d.get("mlp.leconv.weight"))
+    xt = _dev(x)
+    y = ops.FFNBlockFn.apply(xt, d["norm2.weight"], d["norm2.bias"], d["mlp.fc1.weight"], d["mlp.fc1.bias"],
+                             d["mlp.fc2.weight"], d["mlp.fc2.bias"], lew, None, le,
+                             ops.RL_F_PRENORM | ops.RL_F_RESIDUAL)
+    tag = f"ffn/s{stage}/le{le}"
+    _cmp(tag + "/y", y, y_ref)
+    y.backward(g.float().cuda())
+    _cmp(tag + "/dx", xt.grad, dx_ref)
+    for k in gr:
+        _cmp(f"{tag}/d_{k}", d[k].grad, gr[k])
+
+
+@pytest.mark.parametrize("stage", [0, 1, 2, 3])
+def test_patch_merge(ops, stage):
+    rs = np.random.RandomState(300 + stage)
+    C, L, B = O.CHANNELS[stage], O.LENGTHS[stage], 3
+    p = {"norm.weight": 1 + 0.1 * _rand(rs, 2 * C), "norm.bias": 0.1 * _rand(rs, 2 * C),
+         "reduction.weight": _rand(rs, 2 * C, 2 * C, scale=(2 * C) ** -0.5)}
+    x, g = _rand(rs, B, L, C), _rand(rs, B, L // 2, 2 * C)
+    y_ref, saved = O.patch_merge_fwd(x, p)
+    dx_ref, gr = O.patch_merge_bwd(g, saved, p)
+    d = {k: _dev(v) for k, v in p.items()}
+    xt = _dev(x)
+    y = ops.PatchFn.apply(xt, d["norm.weight"], d["norm.bias"], d["reduction.weight"], None, 0)
+    _cmp(f"pm/s{stage}/y", y, y_ref)
+    y.backward(g.float().cuda())
+    _cmp(f"pm/s{stage}/dx", xt.grad, dx_ref)
+    for k in gr:
+        _cmp(f"pm/s{stage}/d_{k}", d[k].grad, gr[k])
+
+
+@pytest.mark.parametrize("stage", [1, 2, 3, 4])
+@pytest.mark.parametrize("with_skip", [True, False])
+def test_patch_separate(ops, stage, with_skip):
+    rs = np.random.RandomState(400 + stage)
+    C, L, B = O.CHANNELS[stage], O.LENGTHS[stage], 3
+    p = {"norm.weight": 1 + 0.1 * _rand(rs, C // 2), "norm.bias": 0.1 * _rand(rs, C // 2),
+         "reduction.weight": _rand(rs, C // 2, C // 2, scale=(C // 2) ** -0.5)}
+    x, g = _rand(rs, B, L, C), _rand(rs, B, 2 * L, C // 2)
+    skip = _rand(rs, B, 2 * L, C // 2) if with_skip else None
+    y_ref, saved = O.patch_separate_fwd(x, p, skip)
+    dx_ref, gr = O.patch_separate_bwd(g, saved, p)
+    d = {k: _dev(v) for k, v in p.items()}
+    xt = _dev(x)
+    st = _dev(skip) if with_skip else None
+    y = ops.PatchFn.apply(xt, d["norm.weight"], d["norm.bias"], d["reduction.weight"], st, 1)
+    tag = f"ps/s{stage}/{'skip' if with_skip else 'noskip'}"
+    _cmp(tag + "/y", y, y_ref)
+    y.backward(g.float().cuda())
+    _cmp(tag + "/dx", xt.grad, dx_ref)
+    if with_skip:
+        _cmp(tag + "/dskip", st.grad, g)
+    for k in gr:
+        _cmp(f"{tag}/d_{k}", d[k].grad, gr[k])
+
+
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("L", [256, 512])
+def test_stem(ops, training, L):
+    rs = np.random.RandomState(500 + L)
+    B = 5
+    p = {"conv1.0.weight": _rand(rs, 8, 2, 3, scale=0.4), "conv1.0.bias": 0.1 * _rand(rs, 8),
+         "conv1.2.weight": 1 + 0.1 * _rand(rs, 8), "conv1.2.bias": 0.1 * _rand(rs, 8),
+         "conv1.2.running_mean": 0.1 * _rand(rs, 8), "conv1.2.running_var": 0.5 + torch.from_numpy(rs.uniform(size=8))}
+    x, g = _rand(rs, B, 2, L), _rand(rs, B, L, 8)
+    y_ref, saved, new_stats = O.stem_fwd(x, p, training)
+    dx_ref, gr = O.stem_bwd(g, saved, p)
+    d = {k: _dev(v, not k.startswith("conv1.2.running")) for k, v in p.items()}
+    nbt = torch.tensor(3, dtype=torch.int64, device="cuda")
+    xt = _dev(x)
+    y = ops.StemFn.apply(xt, d["conv1.0.weight"], d["conv1.0.bias"], d["conv1.2.weight"], d["conv1.2.bias"],
+                         d["conv1.2.running_mean"], d["conv1.2.running_var"], nbt, training, 0.1, 1e-5, None)
+    tag = f"stem/{'train' if training else 'eval'}/L{L}"
+    _cmp(tag + "/y", y, y_ref)
+    if training:
+        _cmp(tag + "/running_mean", d["conv1.2.running_mean"], new_stats[0])
+        _cmp(tag + "/running_var", d["conv1.2.running_var"], new_stats[1])
+        assert int(nbt.item()) == 4
+    else:
+        assert int(nbt.item()) == 3
+    y.backward(g.float().cuda())
+    _cmp(tag + "/dx", xt.grad, dx_ref)
+    for k in gr:
+        _cmp(f"{tag}/d_{k}", d[k].grad, gr[k])
+
+
+def test_head(ops):
+    rs = np.random.RandomState(600)
+    B, L = 4, 256
+    p = {"transconv.0.weight": _rand(rs, 2, 8, 3, scale=0.2), "transconv.0.bias": 0.1 * _rand(rs, 2)}
+    x, skip, dout = _rand(rs, B, L, 8), _rand(rs, B, L, 8), _rand(rs, B, 2, L)
+    out_ref, saved = O.head_fwd(x, skip, p)
+    ds_ref, gr = O.head_bwd(dout, saved, p)
+    d = {k: _dev(v) for k, v in p.items()}
+    xt, st = _dev(x), _dev(skip)
+    out = ops.HeadFn.apply(xt, st, d["transconv.0.weight"], d["transconv.0.bias"])
+    _cmp("head/out", out, out_ref)
+    out.backward(dout.float().cuda())
+    _cmp("head/dx", xt.grad, ds_ref)
+    _cmp("head/dskip", st.grad, ds_ref)
+    for k in gr:
+        _cmp(f"head/d_{k}", d[k].grad, gr[k])
+
+
+@pytest.mark.parametrize("ci,co,act", [(12, 6, True), (6, 2, True), (2, 6, True), (6, 12, False)])
+def test_conv13(ops, ci, co, act):
+    rs = np.random.RandomState(700 + ci)
+    B, L = 3, 256
+    w, b = _rand(rs, co, ci, 13, scale=(13 * ci) ** -0.5), 0.1 * _rand(rs, co)
+    x, dy = _rand(rs, B, ci, L), _rand(rs, B, co, L)
+    c = O.conv1d_fwd(x, w, b)
+    y_ref = O.leaky_relu(c, 0.01) if act else c
+    dc = dy * torch.where(c > 0, torch.ones_like(c), torch.full_like(c, 0.01)) if act else dy
+    dx_ref, dw_ref, db_ref = O.conv1d_bwd(dc, x, w)
+    xt, wt, bt = _dev(x), _dev(w), _dev(b)
+    y = ops.Conv1dFn.apply(xt, wt, bt, act, 0.01)
+    tag = f"conv13/{ci}to{co}"
+    _cmp(tag + "/y", y, y_ref)
+    y.backward(dy.float().cuda())
+    _cmp(tag + "/dx", xt.grad, dx_ref)
+    _cmp(tag + "/dw", wt.grad, dw_ref)
+    _cmp(tag + "/db", bt.grad, db_ref)
+
+
+def test_mse_and_metrics(ops):
+    rs = np.random.RandomState(800)
+    pred, tgt = _rand(rs, 9, 2, 256), _rand(rs, 9, 2, 256)
+    loss_ref, dout_ref = O.mse_loss_fwd_bwd(pred, tgt)
+    loss, dout, rmse, snr = ops.mse_loss_metrics(pred.float().cuda(), tgt.float().cuda())
+    _cmp("mse/loss", loss, loss_ref.reshape(1))
+    _cmp("mse/dout", dout, dout_ref)
+    _cmp("mse/rmse", rmse, O.RMSE(tgt, pred))
+    assert torch.allclose(snr.double().cpu(), O.SNR(tgt, pred), atol=1e-3)     # dB
+    # weighted variant reduces exactly to MSE at w == 1
+    loss_w, dout_w, _, _ = ops.mse_loss_metrics(pred.float().cuda(), tgt.float().cuda(),
+                                                weight=torch.ones(512, device="cuda"))
+    assert torch.equal(loss_w, loss) and torch.equal(dout_w, dout)
+
+
+def test_adam_flat(ops):
+    rs = np.random.RandomState(900)
+    n = 10007
+    p0, g1, g2 = _rand(rs, n), _rand(rs, n), _rand(rs, n)
+    p, m, v = p0.clone(), torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    O.adam_step(p, g1, m, v, 1)
+    O.adam_step(p, g2, m, v, 2)
+    n_pad = (n + 3) // 4 * 4
+    pd = torch.zeros(n_pad, device="cuda"); pd[:n] = p0.float().cuda()
+    md, vd = torch.zeros_like(pd), torch.zeros_like(pd)
+    gd = torch.zeros_like(pd)
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for gg in (g1, g2):
+        gd[:n] = gg.float().cuda()
+        ops.adam_flat(pd, gd, md, vd, step)
+    assert int(step.item()) == 2
+    _cmp("adam/dev_step/p", pd[:n], p, rtol=1e-5)
+    pd2 = torch.zeros(n_pad, device="cuda"); pd2[:n] = p0.float().cuda()
+    md2, vd2 = torch.zeros_like(pd2), torch.zeros_like(pd2)
+    for i, gg in enumerate((g1, g2)):
+        gd[:n] = gg.float().cuda()
+        ops.adam_flat(pd2, gd, md2, vd2, i + 1)
+    _cmp("adam/host_step/p", pd2[:n], p, rtol=1e-5)
+
+
+def test_errors_are_loud(ops):
+    from ecg_denoise_b200 import _lib
+    with pytest.raises(_lib.RalenetError):
+        ops.mse_loss_metrics(torch.zeros(2, 2, 256), torch.zeros(2, 2, 256))            # CPU tensors
+    with pytest.raises(_lib.RalenetError):
+        ops.PatchFn.apply(torch.zeros(1, 100, 8, device="cuda"), torch.ones(16, device="cuda"),
+                          torch.zeros(16, device="cuda"), torch.zeros(16, 16, device="cuda"), None, 0)  # bad shape

@@ -16,14 +16,65 @@ void rl_set_error(const char* fmt, ...) {
 
 void rl_count_launch() { ++g_launches; }
 
-int rl_check_launch(const char* what) {
+// ---- optional per-launch timing (bench.py's roofline pass): one event after every launch on the
+// profiled stream; a kernel's duration is the gap to the previous event (launches are serialised).
+namespace {
+constexpr int kMaxProf = 8192;
+struct Prof {
+  bool on = false;
+  cudaStream_t stream = nullptr;
+  int n = 0;
+  cudaEvent_t ev[kMaxProf + 1];
+  int created = 0;
+  char label[kMaxProf][48];
+};
+Prof g_prof;
+}  // namespace
+
+int rl_check_launch(const char* what, int t0, int t1) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     rl_set_error("%s: %s", what, cudaGetErrorString(e));
     return RL_ERR_CUDA;
   }
   ++g_launches;
+  if (g_prof.on && g_prof.n < kMaxProf) {
+    const int i = g_prof.n++;
+    if (t1 >= 0) snprintf(g_prof.label[i], sizeof(g_prof.label[i]), "%s<%d,%d>", what, t0, t1);
+    else if (t0 >= 0) snprintf(g_prof.label[i], sizeof(g_prof.label[i]), "%s<%d>", what, t0);
+    else snprintf(g_prof.label[i], sizeof(g_prof.label[i]), "%s", what);
+    cudaEventRecord(g_prof.ev[i + 1], g_prof.stream);
+  }
   return RL_OK;
+}
+
+extern "C" int ralenet_profile_begin(void* stream) {
+  while (g_prof.created <= kMaxProf) {
+    if (cudaEventCreate(&g_prof.ev[g_prof.created]) != cudaSuccess) {
+      rl_set_error("profile_begin: cudaEventCreate failed");
+      return RL_ERR_CUDA;
+    }
+    ++g_prof.created;
+  }
+  g_prof.stream = (cudaStream_t)stream;
+  g_prof.n = 0;
+  g_prof.on = true;
+  cudaEventRecord(g_prof.ev[0], g_prof.stream);
+  return RL_OK;
+}
+
+extern "C" int ralenet_profile_end(char* labels, int32_t label_stride, float* ms, int32_t max_n) {
+  g_prof.on = false;
+  const int n = g_prof.n < max_n ? g_prof.n : max_n;
+  if (g_prof.n > 0 && cudaEventSynchronize(g_prof.ev[g_prof.n]) != cudaSuccess) {
+    rl_set_error("profile_end: cudaEventSynchronize failed");
+    return RL_ERR_CUDA;
+  }
+  for (int i = 0; i < n; ++i) {
+    cudaEventElapsedTime(&ms[i], g_prof.ev[i], g_prof.ev[i + 1]);
+    snprintf(labels + (size_t)i * label_stride, label_stride, "%s", g_prof.label[i]);
+  }
+  return n;
 }
 
 extern "C" int ralenet_abi_version(void) { return RL_ABI_VERSION; }

@@ -348,7 +348,7 @@ int launch_fwd(const rl_attn_fwd_args* a, cudaStream_t st) {
     if (int rc = rl_set_smem(attn_fwd_kernel<C, 2>, smem)) return rc;
     attn_fwd_kernel<C, 2><<<a->B, RL_NT, smem, st>>>(*a);
   }
-  return rl_check_launch("attn_fwd_kernel");
+  return rl_check_launch("attn_fwd_kernel", C);
 }
 
 template <int C>
@@ -362,7 +362,7 @@ int launch_bwd(const rl_attn_bwd_args* a, cudaStream_t st) {
     if (int rc = rl_set_smem(attn_bwd_kernel<C, 2>, smem)) return rc;
     attn_bwd_kernel<C, 2><<<a->B, RL_NT, smem, st>>>(*a);
   }
-  return rl_check_launch("attn_bwd_kernel");
+  return rl_check_launch("attn_bwd_kernel", C);
 }
 
 int check_shape(int B, int L, int C, int H, int W, int c0) {

@@ -12,7 +12,7 @@
 
 void rl_set_error(const char* fmt, ...);
 void rl_count_launch();
-int rl_check_launch(const char* what);
+int rl_check_launch(const char* what, int tag0 = -1, int tag1 = -1);
 
 #define RL_REQUIRE(cond, code, ...)            \
   do {                                         \

@@ -322,7 +322,7 @@ int launch_fwd(const rl_ffn_fwd_args* a, cudaStream_t st) {
     if (int rc = rl_set_smem(ffn_fwd_kernel<C, 2>, smem)) return rc;
     ffn_fwd_kernel<C, 2><<<a->B, RL_NT, smem, st>>>(*a);
   }
-  return rl_check_launch("ffn_fwd_kernel");
+  return rl_check_launch("ffn_fwd_kernel", C);
 }
 
 template <int C>
@@ -335,7 +335,7 @@ int launch_bwd(const rl_ffn_bwd_args* a, cudaStream_t st) {
     if (int rc = rl_set_smem(ffn_bwd_kernel<C, 2>, smem)) return rc;
     ffn_bwd_kernel<C, 2><<<a->B, RL_NT, smem, st>>>(*a);
   }
-  return rl_check_launch("ffn_bwd_kernel");
+  return rl_check_launch("ffn_bwd_kernel", C);
 }
 
 int check_shape(int B, int L, int C, int le) {

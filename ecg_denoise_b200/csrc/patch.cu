@@ -122,7 +122,7 @@ int launch_fwd(const rl_patch_fwd_args* a, cudaStream_t st) {
     if (int rc = rl_set_smem(patch_fwd_kernel<CN, 2>, smem)) return rc;
     patch_fwd_kernel<CN, 2><<<a->B, RL_NT, smem, st>>>(*a);
   }
-  return rl_check_launch("patch_fwd_kernel");
+  return rl_check_launch("patch_fwd_kernel", CN);
 }
 
 template <int CN>
@@ -136,7 +136,7 @@ int launch_bwd(const rl_patch_bwd_args* a, float* gsum, cudaStream_t st) {
     if (int rc = rl_set_smem(patch_bwd_kernel<CN, 2>, smem)) return rc;
     patch_bwd_kernel<CN, 2><<<a->B, RL_NT, smem, st>>>(*a, gsum);
   }
-  return rl_check_launch("patch_bwd_kernel");
+  return rl_check_launch("patch_bwd_kernel", CN);
 }
 
 int check_shape(int B, int L, int C, int mode, int* cn) {

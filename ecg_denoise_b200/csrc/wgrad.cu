@@ -80,7 +80,7 @@ int launch(const float* dY, int ldy, const float* X, int ldx, int M, int N, int 
   splits = (M + MC - 1) / MC;
   dim3 grid(tiles, splits);
   wgrad_kernel<TN, TK><<<grid, RL_NT, 0, st>>>(dY, ldy, X, ldx, M, N, K, dW, db, MC);
-  return rl_check_launch("wgrad_kernel");
+  return rl_check_launch("wgrad_kernel", N, K);
 }
 
 template <int TN>
@@ -118,4 +118,10 @@ int rl_launch_wgrad(const float* dY, int ldy, const float* X, int ldx, int M, in
     case 64: return dispatch_k<64>(TK, dY, ldy, X, ldx, M, N, K, dW, db, st);
   }
   return RL_ERR_SHAPE;
+}
+
+extern "C" int ralenet_wgrad(const float* dY, int32_t ldy, const float* X, int32_t ldx, int32_t M, int32_t N, int32_t K,
+                             float* dW, float* db, void* stream) {
+  RL_REQUIRE(dY && X && dW, RL_ERR_NULL, "wgrad: NULL tensor");
+  return rl_launch_wgrad(dY, ldy, X, ldx, M, N, K, dW, db, (cudaStream_t)stream);
 }

@@ -230,7 +230,7 @@ class RalenetFn(torch.autograd.Function):
         plan.refresh_requires_grad()
         net = plan.net
         training = net.training
-        save = torch.is_grad_enabled() and (x.requires_grad or anchor.requires_grad)
+        save = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         ws = torch.empty(workspace_bytes(B, L0, save), device=x.device, dtype=torch.uint8)
         cfg = plan.cfg(B, L0, training, save, ws)
         out = torch.empty(B, 2, L0, device=x.device, dtype=torch.float32)
@@ -301,6 +301,7 @@ class FusedTrainer:
 
     def _setup(self, x: torch.Tensor):
         plan = self.plan
+        _lib.check_device(x.device.index if x.device.index is not None else torch.cuda.current_device())
         plan.ensure(x.device)
         plan.refresh_requires_grad()
         if self.m is None or self.m.numel() != plan.flat.numel() or self.m.device != x.device:
@@ -347,39 +348,58 @@ class FusedTrainer:
         ops.adam_flat(plan.flat, plan.flat_grad, self.m, self.v, self.step_dev, self.lr, self.betas, self.eps, 1.0)
         return loss, rmse, snr, out
 
-    def step(self, x: torch.Tensor, target: torch.Tensor):
-        """one training step on device tensors x, target of shape (B, 2, L).  Returns (loss[1], rmse[B],
-        snr[B], out) as device tensors (no host sync)."""
-        x, target = _chk(x, "x"), _chk(target, "target")
-        if self._static is None or self._static[0].shape != x.shape:
-            self._setup(x)
-            B, _, L0 = x.shape
-            self._ws = torch.empty(workspace_bytes(B, L0, True), device=x.device, dtype=torch.uint8)
-            self._out = torch.empty(B, 2, L0, device=x.device, dtype=torch.float32)
-            self._static = (torch.empty_like(x), torch.empty_like(target))
-            self.graph = None
-        if not self.use_graph:
-            return self._step_impl(x, target)
+    def _prepare(self, shape, device):
+        if self._static is not None and tuple(self._static[0].shape) == tuple(shape):
+            return
+        B, _, L0 = shape
+        probe = torch.empty(0, device=device)
+        self._setup(probe)
+        self._ws = torch.empty(workspace_bytes(B, L0, True), device=device, dtype=torch.uint8)
+        self._out = torch.empty(B, 2, L0, device=device, dtype=torch.float32)
+        self._static = (torch.empty(shape, device=device, dtype=torch.float32),
+                        torch.empty(shape, device=device, dtype=torch.float32))
+        self.graph = None
+
+    def _replay(self):
         sx, st_ = self._static
-        sx.copy_(x, non_blocking=True)
-        st_.copy_(target, non_blocking=True)
         if self.graph is None:
             # warm up on a side stream (also initialises NCCL communicators), then capture
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
+            bn = self.net.conv1[2]
             snap = (self.plan.flat.clone(), self.m.clone(), self.v.clone(), self.step_dev.clone(),
-                    self.net.conv1[2].running_mean.clone(), self.net.conv1[2].running_var.clone(),
-                    self.net.conv1[2].num_batches_tracked.clone())
+                    bn.running_mean.clone(), bn.running_var.clone(), bn.num_batches_tracked.clone())
             with torch.cuda.stream(s):
                 self._step_impl(sx, st_)
             torch.cuda.current_stream().wait_stream(s)
             # undo the warm-up step so that capture + replay applies exactly one update per call
-            bn = self.net.conv1[2]
             self.plan.flat.copy_(snap[0]); self.m.copy_(snap[1]); self.v.copy_(snap[2]); self.step_dev.copy_(snap[3])
             bn.running_mean.copy_(snap[4]); bn.running_var.copy_(snap[5]); bn.num_batches_tracked.copy_(snap[6])
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._graph_out = self._step_impl(sx, st_)
-            # capture does not execute: replay below performs the step
+            # capture does not execute: the replay below performs the step
         self.graph.replay()
         return self._graph_out
+
+    def step(self, x: torch.Tensor, target: torch.Tensor):
+        """one training step on DEVICE tensors x, target of shape (B, 2, L).  Returns (loss[1], rmse[B], snr[B],
+        out) as device tensors (no host sync)."""
+        x, target = _chk(x, "x"), _chk(target, "target")
+        self._prepare(x.shape, x.device)
+        if not self.use_graph:
+            return self._step_impl(x, target)
+        sx, st_ = self._static
+        sx.copy_(x, non_blocking=True)
+        st_.copy_(target, non_blocking=True)
+        return self._replay()
+
+    def step_host(self, hx: torch.Tensor, ht: torch.Tensor) -> torch.Tensor:
+        """one training step from (pinned) HOST tensors: async H2D of the batch into the static device buffers,
+        then the step; returns the device loss tensor (the caller's .item() is the D2H read)."""
+        dev = next(self.net.parameters()).device
+        self._prepare(hx.shape, dev)
+        sx, st_ = self._static
+        sx.copy_(hx, non_blocking=True)
+        st_.copy_(ht, non_blocking=True)
+        return (self._replay() if self.use_graph else self._step_impl(sx, st_))[0]

@@ -158,7 +158,7 @@ class MSAttention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
         self.softmax = nn.Softmax(dim=-1)
 
-    def _apply(self, x, mask, norm: Optional[nn.LayerNorm], flags: int):
+    def _run(self, x, mask, norm: Optional[nn.LayerNorm], flags: int):
         table, W, c0 = None, 0, 0
         if mask is not None:
             src = getattr(mask, "_rw_src", None)
@@ -175,7 +175,7 @@ class MSAttention(nn.Module):
     def forward(self, x, attn_kv=None, mask=None):
         if attn_kv is not None:
             _unsupported("cross attention (attn_kv)")
-        return self._apply(x, mask, None, 0)
+        return self._run(x, mask, None, 0)
 
 
 class TransformerBlock(nn.Module):
@@ -208,7 +208,7 @@ class TransformerBlock(nn.Module):
 
     def forward_part1(self, x, mask):
         """attention branch WITHOUT the residual (reference :383-390)."""
-        return self.attn._apply(x, mask, self.norm1, ops.RL_F_PRENORM)
+        return self.attn._run(x, mask, self.norm1, ops.RL_F_PRENORM)
 
     def forward_part2(self, x):
         """feed-forward branch WITHOUT the residual (reference :392-395)."""
@@ -218,7 +218,7 @@ class TransformerBlock(nn.Module):
                                     m.fc2.bias, lew, None, mode, ops.RL_F_PRENORM)
 
     def forward(self, x, mask=None):
-        x = self.attn._apply(x, mask, self.norm1, ops.RL_F_PRENORM | ops.RL_F_RESIDUAL)
+        x = self.attn._run(x, mask, self.norm1, ops.RL_F_PRENORM | ops.RL_F_RESIDUAL)
         m = self.mlp
         mode, lew = m._le()
         return ops.FFNBlockFn.apply(x, self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight,

@@ -78,8 +78,7 @@ class AttnBlockFn(torch.autograd.Function):
     def forward(ctx, x, ln_w, ln_b, wq, bq, wkv, bkv, wp, bp, table, H, W, c0, flags):
         x = _chk(x, "x")
         B, L, C = x.shape
-        need = torch.is_grad_enabled() and any(
-            t is not None and t.requires_grad for t in (x, ln_w, ln_b, wq, bq, wkv, bkv, wp, bp, table))
+        need = any(ctx.needs_input_grad)
         y = torch.empty_like(x)
         q = k = v = o = lse = None
         if need:
@@ -129,8 +128,7 @@ class FFNBlockFn(torch.autograd.Function):
     def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, lew, extra, le_mode, flags):
         x = _chk(x, "x")
         B, L, C = x.shape
-        need = torch.is_grad_enabled() and any(
-            t is not None and t.requires_grad for t in (x, ln_w, ln_b, w1, b1, w2, b2, lew, extra))
+        need = any(ctx.needs_input_grad)
         y = torch.empty_like(x)
         h = torch.empty(B, L, 4 * C, device=x.device, dtype=torch.float32) if need else None
         if extra is not None:
@@ -173,7 +171,7 @@ class PatchFn(torch.autograd.Function):
     def forward(ctx, x, ln_w, ln_b, w, skip, mode):
         x = _chk(x, "x")
         B, L, C = x.shape
-        need = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, ln_w, ln_b, w, skip))
+        need = any(ctx.needs_input_grad)
         shape = (B, L // 2, 2 * C) if mode == 0 else (B, 2 * L, C // 2)
         y = torch.empty(shape, device=x.device, dtype=torch.float32)
         u = torch.empty_like(y) if need else None

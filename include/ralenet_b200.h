@@ -314,6 +314,18 @@ int ralenet_net_bwd(const rl_net_cfg* cfg, const rl_net_ptrs* P, const rl_net_pt
 int ralenet_net_bwd_stem(const rl_net_cfg* cfg, const rl_net_ptrs* P, const rl_net_ptrs* G,
                          const float* x, float* dx, void* stream);
 
+/* Weight-gradient GEMM over the token dimension (used by every *_bwd above; exported for benchmarks):
+ *   dW[n*K + k] += sum_m dY[m*ldy + n] * X[m*ldx + k],   db[n] += sum_m dY[m*ldy + n]   (db may be NULL) */
+int ralenet_wgrad(const float* dY, int32_t ldy, const float* X, int32_t ldx, int32_t M, int32_t N, int32_t K,
+                  float* dW, float* db, void* stream);
+
+/* Per-launch timing for bench.py's roofline pass: after ralenet_profile_begin(stream) every kernel this
+ * library launches is followed by a CUDA event on `stream`; ralenet_profile_end() waits for the last one and
+ * returns the number of launches, their labels ("kernel<C>", label_stride bytes each) and durations in ms.
+ * Not thread-safe; do not use while capturing a CUDA graph. */
+int ralenet_profile_begin(void* stream);
+int ralenet_profile_end(char* labels, int32_t label_stride, float* ms, int32_t max_n);
+
 /* number of kernels launched by this library on the calling thread since the last reset
  * (bench.py's gpu_launches). */
 int64_t ralenet_launch_count(int32_t reset);

@@ -270,7 +270,8 @@ def test_mse_and_metrics(ops):
     # weighted variant reduces exactly to MSE at w == 1
     loss_w, dout_w, _, _ = ops.mse_loss_metrics(pred.float().cuda(), tgt.float().cuda(),
                                                 weight=torch.ones(512, device="cuda"))
-    assert torch.equal(loss_w, loss) and torch.equal(dout_w, dout)
+    assert torch.equal(dout_w, dout)
+    assert torch.allclose(loss_w, loss, rtol=1e-6)        # the loss is summed with fp32 atomics across CTAs
 
 
 def test_adam_flat(ops):

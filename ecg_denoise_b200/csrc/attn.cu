@@ -14,20 +14,25 @@
 namespace {
 
 template <int C>
-size_t attn_fwd_smem(int L) { return sizeof(float) * ((size_t)L * lda_of<C>() + 3 * (size_t)L * C + SW_FLOATS + 128); }
+__host__ __device__ constexpr int attn_fwd_swf() {
+  return cmax(WStream<3 * C, C, B_NK>::FLOATS, WStream<C, C, B_NK>::FLOATS);
+}
+template <int C>
+size_t attn_fwd_smem(int L) { return sizeof(float) * (4 * (size_t)L * ld_mk(C) + attn_fwd_swf<C>() + 128); }
 
 // ---------------------------------------------------------------------------------------------
 template <int C, int WIN>
 __global__ void __launch_bounds__(RL_NT) attn_fwd_kernel(const rl_attn_fwd_args a) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int LDA = lda_of<C>();
-  const int L = a.L, H = a.H, W = a.W, c0 = a.c0;
+  constexpr int L = 2048 * WIN / C, H = C / RL_HD;
+  constexpr int LDC = ld_mk(C);
+  const int W = a.W, c0 = a.c0;
   float* su = smem;
-  float* sq = su + L * LDA;
-  float* sk = sq + L * C;
-  float* sv = sk + L * C;
-  float* sw = sv + L * C;
-  float* stab = sw + SW_FLOATS;
+  float* sq = su + L * LDC;
+  float* sk = sq + L * LDC;
+  float* sv = sk + L * LDC;
+  float* sw = sv + L * LDC;
+  float* stab = sw + attn_fwd_swf<C>();
   const int tid = threadIdx.x;
   const size_t woff = (size_t)blockIdx.x * L * C;
   const float* xw = a.x + woff;
@@ -40,43 +45,35 @@ __global__ void __launch_bounds__(RL_NT) attn_fwd_kernel(const rl_attn_fwd_args 
     const float* lb = a.ln_b;
     ln_forward_rows<C>(
         L, [&](int t, int c) { return fmaf(__ldg(xw + t * C + c), sc, __ldg(pe + t * C + c)); },
-        [&](int t, int c, float zh) { su[t * LDA + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c)); });
+        [&](int t, int c, float zh) { su[t * LDC + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c)); });
   } else {
-    for (int i = tid; i < L * C; i += RL_NT) su[(i / C) * LDA + (i % C)] = __ldg(xw + i);
+    copy_rows_g2s(su, LDC, xw, L, C);
   }
   if (W > 0)
     for (int i = tid; i < (2 * W - 1) * H; i += RL_NT) stab[i] = __ldg(a.table + i) * RL_LOG2E;
   __syncthreads();
 
-  // 2. [q|k|v] = u [Wq;Wkv]^T + b   (N = 3C, K = C), weights streamed through sw in K chunks
+  // 2. [q|k|v] = u [Wq;Wkv]^T + b   (N = 3C, K = C): tensor-core GEMM, weights streamed through sw in K chunks
   {
-    TileAcc<4 * WIN, 6> acc;
-    acc.init(L, 3 * C);
-    const int ldd = 3 * C + 1;
-    const int KC = min(C, pow2_floor(SW_FLOATS / ldd));
-    for (int k0 = 0; k0 < C; k0 += KC) {
-      stage_wT(sw, ldd, a.wq, C, 0, C, k0, KC);
-      stage_wT(sw + C, ldd, a.wkv, C, 0, 2 * C, k0, KC);
-      __syncthreads();
-      acc.mac(su + k0, LDA, 1, sw, ldd, KC);
-      __syncthreads();
-    }
+    MmaTile<L, 3 * C> acc;
+    acc.init();
+    WStream<3 * C, C, B_NK>::run(acc, su, LDC, sw, a.wq, C, a.wkv, C);
     const float* bq = a.bq;
     const float* bkv = a.bkv;
     acc.epilogue([&](int t, int n, float v) {
       if (n < C) {
-        sq[t * C + n] = v + (bq ? __ldg(bq + n) : 0.f);
+        sq[t * LDC + n] = v + (bq ? __ldg(bq + n) : 0.f);
       } else {
         v += bkv ? __ldg(bkv + n - C) : 0.f;
-        if (n < 2 * C) sk[t * C + n - C] = v; else sv[t * C + n - 2 * C] = v;
+        if (n < 2 * C) sk[t * LDC + n - C] = v; else sv[t * LDC + n - 2 * C] = v;
       }
     });
   }
   __syncthreads();
   if (a.q) {
-    copy_s2g(a.q + woff, sq, L * C);
-    copy_s2g(a.k + woff, sk, L * C);
-    copy_s2g(a.v + woff, sv, L * C);
+    copy_rows_s2g(a.q + woff, sq, LDC, L, C);
+    copy_rows_s2g(a.k + woff, sk, LDC, L, C);
+    copy_rows_s2g(a.v + woff, sv, LDC, L, C);
   }
 
   // 3. attention core: one (head, query) row per thread, online softmax in the log2 domain.
@@ -84,7 +81,7 @@ __global__ void __launch_bounds__(RL_NT) attn_fwd_kernel(const rl_attn_fwd_args 
   const float qs = 0.5f * RL_LOG2E;                  // head_dim^-0.5 (transformer.py:278) * log2(e)
   for (int item = tid; item < H * L; item += RL_NT) {
     const int i = item % L, h = item / L;
-    float4 q4 = *reinterpret_cast<const float4*>(sq + i * C + 4 * h);
+    float4 q4 = *reinterpret_cast<const float4*>(sq + i * LDC + 4 * h);
     q4.x *= qs; q4.y *= qs; q4.z *= qs; q4.w *= qs;
     const bool central = (W > 0) && ((unsigned)(i - c0) < (unsigned)W);
     float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
@@ -94,7 +91,7 @@ __global__ void __launch_bounds__(RL_NT) attn_fwd_kernel(const rl_attn_fwd_args 
       float s[8];
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
-        const float4 k4 = *reinterpret_cast<const float4*>(kp + (j0 + jj) * C);
+        const float4 k4 = *reinterpret_cast<const float4*>(kp + (j0 + jj) * LDC);
         s[jj] = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
       }
       if (central) {
@@ -113,31 +110,24 @@ __global__ void __launch_bounds__(RL_NT) attn_fwd_kernel(const rl_attn_fwd_args 
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const float p = exp2f(s[jj] - mn);
-        const float4 v4 = *reinterpret_cast<const float4*>(vp + (j0 + jj) * C);
+        const float4 v4 = *reinterpret_cast<const float4*>(vp + (j0 + jj) * LDC);
         l += p;
         o0 = fmaf(p, v4.x, o0); o1 = fmaf(p, v4.y, o1); o2 = fmaf(p, v4.z, o2); o3 = fmaf(p, v4.w, o3);
       }
       m = mn;
     }
     const float inv = 1.0f / l;
-    *reinterpret_cast<float4*>(sq + i * C + 4 * h) = make_float4(o0 * inv, o1 * inv, o2 * inv, o3 * inv);
+    *reinterpret_cast<float4*>(sq + i * LDC + 4 * h) = make_float4(o0 * inv, o1 * inv, o2 * inv, o3 * inv);
     if (a.lse) a.lse[(size_t)blockIdx.x * H * L + item] = m + log2f(l);
   }
   __syncthreads();
-  if (a.o) copy_s2g(a.o + woff, sq, L * C);
+  if (a.o) copy_rows_s2g(a.o + woff, sq, LDC, L, C);
 
   // 4. y = x + o Wp^T + bp        (transformer.py:320, :405)
   {
-    TileAcc<4 * WIN, 2> acc;
-    acc.init(L, C);
-    const int ldd = C + 1;
-    const int KC = min(C, pow2_floor(SW_FLOATS / ldd));
-    for (int k0 = 0; k0 < C; k0 += KC) {
-      stage_wT(sw, ldd, a.wp, C, 0, C, k0, KC);
-      __syncthreads();
-      acc.mac(sq + k0, C, 1, sw, ldd, KC);
-      __syncthreads();
-    }
+    MmaTile<L, C> acc;
+    acc.init();
+    WStream<C, C, B_NK>::run(acc, sq, LDC, sw, a.wp, C, nullptr, C);
     const float* bp = a.bp;
     float* yw = a.y + woff;
     const bool resid = a.flags & RL_F_RESIDUAL;
@@ -151,29 +141,30 @@ __global__ void __launch_bounds__(RL_NT) attn_fwd_kernel(const rl_attn_fwd_args 
 
 // ---------------------------------------------------------------------------------------------
 template <int C>
+__host__ __device__ constexpr int attn_bwd_swf() { return WStream<C, C, B_KN>::FLOATS; }
+template <int C>
 size_t attn_bwd_smem(int L) {
-  return sizeof(float) * (7 * (size_t)L * C + 2 * ((size_t)L * C / 4) + (size_t)L * lda_of<C>() + SW_FLOATS + 256 +
-                          2 * C);
+  return sizeof(float) * (8 * (size_t)L * ld_mk(C) + 2 * ((size_t)L * C / 4) + attn_bwd_swf<C>() + 256 + 2 * C);
 }
 
 template <int C, int WIN>
 __global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args a) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int LDA = lda_of<C>();
-  const int L = a.L, H = a.H, W = a.W, c0 = a.c0;
-  const int LC = L * C;
+  constexpr int L = 2048 * WIN / C, H = C / RL_HD;
+  constexpr int LDC = ld_mk(C), LC = L * C, LP = L * LDC;
+  const int W = a.W, c0 = a.c0;
   float* sq = smem;
-  float* sk = sq + LC;
-  float* sv = sk + LC;
-  float* sdo = sv + LC;
-  float* sdq = sdo + LC;
-  float* sdk = sdq + LC;
-  float* sdv = sdk + LC;
-  float* sD = sdv + LC;
+  float* sk = sq + LP;
+  float* sv = sk + LP;
+  float* sdo = sv + LP;
+  float* sdq = sdo + LP;
+  float* sdk = sdq + LP;
+  float* sdv = sdk + LP;
+  float* su = sdv + LP;
+  float* sD = su + LP;
   float* sLse = sD + LC / 4;
-  float* su = sLse + LC / 4;
-  float* sw = su + L * LDA;
-  float* stab = sw + SW_FLOATS;
+  float* sw = sLse + LC / 4;
+  float* stab = sw + attn_bwd_swf<C>();
   float* stabg = stab + 128;
   float* s_gb = stabg + 128;
   const int tid = threadIdx.x;
@@ -182,11 +173,11 @@ __global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args 
   const float* xw = a.x + woff;
 
   // 1. stage saved tensors; g -> sdq (temp), o -> sdk (temp)
-  copy_g2s(sq, a.q + woff, LC);
-  copy_g2s(sk, a.k + woff, LC);
-  copy_g2s(sv, a.v + woff, LC);
-  copy_g2s(sdq, gw, LC);
-  copy_g2s(sdk, a.o + woff, LC);
+  copy_rows_g2s(sq, LDC, a.q + woff, L, C);
+  copy_rows_g2s(sk, LDC, a.k + woff, L, C);
+  copy_rows_g2s(sv, LDC, a.v + woff, L, C);
+  copy_rows_g2s(sdq, LDC, gw, L, C);
+  copy_rows_g2s(sdk, LDC, a.o + woff, L, C);
   copy_g2s(sLse, a.lse + (size_t)blockIdx.x * (LC / 4), LC / 4);
   if (tid < 128) {
     stabg[tid] = 0.f;
@@ -195,26 +186,19 @@ __global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args 
   for (int i = tid; i < 2 * C; i += RL_NT) s_gb[i] = 0.f;
   __syncthreads();
 
-  // 2. do = g Wp            (dgrad of proj; B(k,n) = Wp[k][n] natural layout)
+  // 2. do = g Wp            (dgrad of proj; B(k,n) = Wp[k][n], natural layout)
   {
-    TileAcc<4 * WIN, 2> acc;
-    acc.init(L, C);
-    const int ldd = C + 1;
-    const int KC = min(C, pow2_floor(SW_FLOATS / ldd));
-    for (int k0 = 0; k0 < C; k0 += KC) {
-      stage_w(sw, ldd, a.wp, C, k0, KC, 0, C);
-      __syncthreads();
-      acc.mac(sdq + k0, C, 1, sw, ldd, KC);
-      __syncthreads();
-    }
-    acc.epilogue([&](int t, int n, float v) { sdo[t * C + n] = v; });
+    MmaTile<L, C> acc;
+    acc.init();
+    WStream<C, C, B_KN>::run(acc, sdq, LDC, sw, a.wp, 0, nullptr, C);
+    acc.epilogue([&](int t, int n, float v) { sdo[t * LDC + n] = v; });
   }
   __syncthreads();
   // 3. D[h,i] = do_i . o_i
   for (int item = tid; item < H * L; item += RL_NT) {
     const int i = item % L, h = item / L;
-    const float4 d4 = *reinterpret_cast<const float4*>(sdo + i * C + 4 * h);
-    const float4 o4 = *reinterpret_cast<const float4*>(sdk + i * C + 4 * h);
+    const float4 d4 = *reinterpret_cast<const float4*>(sdo + i * LDC + 4 * h);
+    const float4 o4 = *reinterpret_cast<const float4*>(sdk + i * LDC + 4 * h);
     sD[item] = d4.x * o4.x + d4.y * o4.y + d4.z * o4.z + d4.w * o4.w;
   }
   __syncthreads();
@@ -223,17 +207,17 @@ __global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args 
   // 4a. dq: one (head, query) row per thread
   for (int item = tid; item < H * L; item += RL_NT) {
     const int i = item % L, h = item / L;
-    float4 q4 = *reinterpret_cast<const float4*>(sq + i * C + 4 * h);
+    float4 q4 = *reinterpret_cast<const float4*>(sq + i * LDC + 4 * h);
     q4.x *= qs; q4.y *= qs; q4.z *= qs; q4.w *= qs;
-    const float4 d4 = *reinterpret_cast<const float4*>(sdo + i * C + 4 * h);
+    const float4 d4 = *reinterpret_cast<const float4*>(sdo + i * LDC + 4 * h);
     const float Di = sD[item], lse = sLse[item];
     const bool central = (W > 0) && ((unsigned)(i - c0) < (unsigned)W);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     const float* kp = sk + 4 * h;
     const float* vp = sv + 4 * h;
     for (int j = 0; j < L; ++j) {
-      const float4 k4 = *reinterpret_cast<const float4*>(kp + j * C);
-      const float4 v4 = *reinterpret_cast<const float4*>(vp + j * C);
+      const float4 k4 = *reinterpret_cast<const float4*>(kp + j * LDC);
+      const float4 v4 = *reinterpret_cast<const float4*>(vp + j * LDC);
       float s = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
       const bool cpair = central && ((unsigned)(j - c0) < (unsigned)W);
       if (cpair) s += stab[(i - j + W - 1) * H + h];
@@ -243,14 +227,13 @@ __global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args 
       a0 = fmaf(ds, k4.x, a0); a1 = fmaf(ds, k4.y, a1); a2 = fmaf(ds, k4.z, a2); a3 = fmaf(ds, k4.w, a3);
       if (cpair && a.d_table) atomicAdd(&stabg[(i - j + W - 1) * H + h], ds);
     }
-    *reinterpret_cast<float4*>(sdq + i * C + 4 * h) = make_float4(0.5f * a0, 0.5f * a1, 0.5f * a2, 0.5f * a3);
+    *reinterpret_cast<float4*>(sdq + i * LDC + 4 * h) = make_float4(0.5f * a0, 0.5f * a1, 0.5f * a2, 0.5f * a3);
   }
-  // 4b. dk, dv: one (head, key) column per thread  (sdq is not read here, sdk/sdv are only written)
-  __syncthreads();   // sdk (o) was read in step 3 by other threads; step 4a done with sdq writes
+  // 4b. dk, dv: one (head, key) column per thread (sdk held o, last read in step 3 before a barrier)
   for (int item = tid; item < H * L; item += RL_NT) {
     const int j = item % L, h = item / L;
-    const float4 k4 = *reinterpret_cast<const float4*>(sk + j * C + 4 * h);
-    const float4 v4 = *reinterpret_cast<const float4*>(sv + j * C + 4 * h);
+    const float4 k4 = *reinterpret_cast<const float4*>(sk + j * LDC + 4 * h);
+    const float4 v4 = *reinterpret_cast<const float4*>(sv + j * LDC + 4 * h);
     const bool centralj = (W > 0) && ((unsigned)(j - c0) < (unsigned)W);
     float k0a = 0.f, k1a = 0.f, k2a = 0.f, k3a = 0.f, v0a = 0.f, v1a = 0.f, v2a = 0.f, v3a = 0.f;
     const float* qp = sq + 4 * h;
@@ -258,8 +241,8 @@ __global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args 
     const float* Dp = sD + h * L;
     const float* Lp = sLse + h * L;
     for (int i = 0; i < L; ++i) {
-      const float4 q4 = *reinterpret_cast<const float4*>(qp + i * C);
-      const float4 d4 = *reinterpret_cast<const float4*>(dp_ + i * C);
+      const float4 q4 = *reinterpret_cast<const float4*>(qp + i * LDC);
+      const float4 d4 = *reinterpret_cast<const float4*>(dp_ + i * LDC);
       float s = qs * (q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w);
       if (centralj && ((unsigned)(i - c0) < (unsigned)W)) s += stab[(i - j + W - 1) * H + h];
       const float p = exp2f(s - Lp[i]);
@@ -268,8 +251,8 @@ __global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args 
       const float ds = p * (dpv - Dp[i]);
       k0a = fmaf(ds, q4.x, k0a); k1a = fmaf(ds, q4.y, k1a); k2a = fmaf(ds, q4.z, k2a); k3a = fmaf(ds, q4.w, k3a);
     }
-    *reinterpret_cast<float4*>(sdk + j * C + 4 * h) = make_float4(0.5f * k0a, 0.5f * k1a, 0.5f * k2a, 0.5f * k3a);
-    *reinterpret_cast<float4*>(sdv + j * C + 4 * h) = make_float4(v0a, v1a, v2a, v3a);
+    *reinterpret_cast<float4*>(sdk + j * LDC + 4 * h) = make_float4(0.5f * k0a, 0.5f * k1a, 0.5f * k2a, 0.5f * k3a);
+    *reinterpret_cast<float4*>(sdv + j * LDC + 4 * h) = make_float4(v0a, v1a, v2a, v3a);
   }
   __syncthreads();
 
@@ -280,27 +263,20 @@ __global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args 
     for (int i = tid; i < 3 * L * C4; i += RL_NT) {
       const int c4 = i % C4, seg = (i / C4) % 3, t = i / (3 * C4);
       const float* src = (seg == 0) ? sdq : (seg == 1) ? sdk : sdv;
-      reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src + t * C)[c4];
+      reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src + t * LDC)[c4];
     }
   }
 
   // 6. du = dq Wq + dk Wk + dv Wv       (K = 3C in three segments)
   {
-    TileAcc<4 * WIN, 2> acc;
-    acc.init(L, C);
-    const int ldd = C + 1;
-    const int KC = min(C, pow2_floor(SW_FLOATS / ldd));
+    MmaTile<L, C> acc;
+    acc.init();
     for (int seg = 0; seg < 3; ++seg) {
       const float* As = (seg == 0) ? sdq : (seg == 1) ? sdk : sdv;
       const float* Wsrc = (seg == 0) ? a.wq : (seg == 1) ? a.wkv : a.wkv + (size_t)C * C;
-      for (int k0 = 0; k0 < C; k0 += KC) {
-        stage_w(sw, ldd, Wsrc, C, k0, KC, 0, C);
-        __syncthreads();
-        acc.mac(As + k0, C, 1, sw, ldd, KC);
-        __syncthreads();
-      }
+      WStream<C, C, B_KN>::run(acc, As, LDC, sw, Wsrc, 0, nullptr, C);
     }
-    acc.epilogue([&](int t, int n, float v) { su[t * LDA + n] = v; });
+    acc.epilogue([&](int t, int n, float v) { su[t * LDC + n] = v; });
   }
   __syncthreads();
 
@@ -315,7 +291,7 @@ __global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args 
     const float* lb = a.ln_b;
     ln_backward_rows<C>(
         L, lw, s_gb, [&](int t, int c) { return fmaf(__ldg(xw + t * C + c), sc, __ldg(pe + t * C + c)); },
-        [&](int t, int c) { return su[t * LDA + c]; },
+        [&](int t, int c) { return su[t * LDC + c]; },
         [&](int t, int c, float dz, float zh) {
           dxw[t * C + c] = (resid ? __ldg(gw + t * C + c) : 0.f) + sc * dz;
           uw[t * C + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c));
@@ -329,7 +305,7 @@ __global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args 
   } else {
     for (int i = tid; i < LC; i += RL_NT) {
       const int t = i / C, c = i % C;
-      dxw[i] = su[t * LDA + c] + (resid ? __ldg(gw + i) : 0.f);
+      dxw[i] = su[t * LDC + c] + (resid ? __ldg(gw + i) : 0.f);
       uw[i] = __ldg(xw + i);
     }
   }
@@ -415,8 +391,8 @@ extern "C" int ralenet_attn_bwd(const rl_attn_bwd_args* a, void* stream) {
   }
   if (rc) return rc;
   const int M = a->B * a->L, C = a->C;
-  if ((rc = rl_launch_wgrad(a->g, C, a->o, C, M, C, C, a->d_wp, a->d_bp, st))) return rc;
-  if ((rc = rl_launch_wgrad(a->dqkv, 3 * C, a->u, C, M, C, C, a->d_wq, a->d_bq, st))) return rc;
-  if ((rc = rl_launch_wgrad(a->dqkv + C, 3 * C, a->u, C, M, 2 * C, C, a->d_wkv, a->d_bkv, st))) return rc;
-  return RL_OK;
+  const RlWgradDesc d[3] = {{a->g, C, a->o, C, C, C, a->d_wp, a->d_bp},
+                            {a->dqkv, 3 * C, a->u, C, C, C, a->d_wq, a->d_bq},
+                            {a->dqkv + C, 3 * C, a->u, C, 2 * C, C, a->d_wkv, a->d_bkv}};
+  return rl_launch_wgrad_group(d, 3, M, st);
 }

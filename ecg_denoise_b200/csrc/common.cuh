@@ -40,6 +40,13 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * __expf(-0.5f * x * x) * 0.3989422804014327f;
 }
 
+// gelu(x) and gelu'(x) sharing one erf evaluation
+__device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  g = x * cdf;
+  dg = cdf + x * __expf(-0.5f * x * x) * 0.3989422804014327f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -264,8 +271,240 @@ __device__ __forceinline__ int pow2_floor(int v) {
 template <int C>
 __host__ __device__ constexpr int lda_of() { return C + 1; }   // odd row stride: conflict-free A operand
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core CTA GEMM on shared-memory operands: legacy mma.sync m16n8k8 TF32 with the 3xTF32 split
+// (a = a_hi + a_lo, D += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi), which keeps fp32-grade accuracy
+// (the north star's 1e-3 tolerance leaves no room for single-pass TF32 through 18 blocks).
+// Measured on this B200 (profiles/mma_rate_b200.txt): mma.sync TF32 277 TFLOP/s vs FFMA 72 TFLOP/s.
+//
+// out[M x N] is spread over the 8 warps; each warp owns RT x CT m16n8 tiles.  Operand layouts:
+//   A_MK: A(m,k) at A[m*lda + k]  (conflict-free when lda % 8 == 4)    A_KM: A[k*lda + m]  (lda % 32 in {8,24})
+//   B_NK: B(k,n) at B[n*ldb + k]  (ldb % 8 == 4)                       B_KN: B[k*ldb + n]  (ldb % 32 in {8,24})
+enum { A_MK = 0, A_KM = 1 };
+enum { B_NK = 0, B_KN = 1 };
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// x = hi + lo exactly; hi has a 10-bit mantissa (truncated), lo is fed as is (the MMA ignores its low 13 bits)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+template <int M, int N>
+struct MmaTile {
+  static constexpr int MT = M / 16, NT = N / 8, NW = RL_NT / 32;
+  static_assert(M % 16 == 0 && N % 8 == 0, "MmaTile: M % 16 and N % 8");
+  static_assert((MT * NT) % NW == 0, "MmaTile: tiles must divide over the warps");
+  static constexpr int TPW = MT * NT / NW;
+  static constexpr int CT = (NT < TPW) ? NT : TPW;
+  static constexpr int RT = TPW / CT;
+  static_assert(TPW % CT == 0 && NT % CT == 0 && MT % RT == 0, "MmaTile: warp tiling");
+  static constexpr int WN = NT / CT;
+  float acc[RT][CT][4];
+  int row0, col0;
+
+  __device__ __forceinline__ void init() {
+    const int warp = threadIdx.x >> 5;
+    row0 = (warp / WN) * RT * 16;
+    col0 = (warp % WN) * CT * 8;
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[r][c][e] = 0.f;
+  }
+
+  // acc += A[:, 0:K] * B[0:K, :]   (K % 8 == 0; A and B point at k = 0 of the chunk)
+  template <int AL, int BL>
+  __device__ __forceinline__ void mac(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                      int K) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      uint32_t ahi[RT][4], alo[RT][4];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const int m = row0 + r * 16 + g;
+        float a0, a1, a2, a3;
+        if (AL == A_MK) {
+          const float* p = A + m * lda + k0 + t;
+          a0 = p[0]; a1 = p[8 * lda]; a2 = p[4]; a3 = p[8 * lda + 4];
+        } else {
+          const float* p = A + (k0 + t) * lda + m;
+          a0 = p[0]; a1 = p[8]; a2 = p[4 * lda]; a3 = p[4 * lda + 8];
+        }
+        split_tf32(a0, ahi[r][0], alo[r][0]);
+        split_tf32(a1, ahi[r][1], alo[r][1]);
+        split_tf32(a2, ahi[r][2], alo[r][2]);
+        split_tf32(a3, ahi[r][3], alo[r][3]);
+      }
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const int n = col0 + c * 8 + g;
+        float b0, b1;
+        if (BL == B_NK) {
+          const float* p = B + n * ldb + k0 + t;
+          b0 = p[0]; b1 = p[4];
+        } else {
+          const float* p = B + (k0 + t) * ldb + n;
+          b0 = p[0]; b1 = p[4 * ldb];
+        }
+        uint32_t bhi[2], blo[2];
+        split_tf32(b0, bhi[0], blo[0]);
+        split_tf32(b1, bhi[1], blo[1]);
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          mma_tf32(acc[r][c], alo[r], bhi);
+          mma_tf32(acc[r][c], ahi[r], blo);
+          mma_tf32(acc[r][c], ahi[r], bhi);
+        }
+      }
+    }
+  }
+
+  // f(row, col, value) for every output element owned by this thread
+  template <class F>
+  __device__ __forceinline__ void epilogue(F f) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const int m = row0 + r * 16 + g, n = col0 + c * 8 + 2 * t;
+        f(m, n, acc[r][c][0]);
+        f(m, n + 1, acc[r][c][1]);
+        f(m + 8, n, acc[r][c][2]);
+        f(m + 8, n + 1, acc[r][c][3]);
+      }
+  }
+};
+
+// shared-memory row strides that make the fragment loads of MmaTile conflict-free
+__host__ __device__ constexpr int ld_mk(int K) { return K + 4; }                        // A_MK / B_NK: ld % 8 == 4
+__host__ __device__ constexpr int ld_kn(int N) { return (N % 32 == 0) ? N + 8 : (N == 16 ? 24 : 40); }   // A_KM / B_KN
+// largest power-of-two K chunk (>= 8) such that rows*(chunk+4) (B_NK) fits `budget` floats
+__host__ __device__ constexpr int kc_nk(int N, int K, int budget) {
+  int kc = K;
+  while (kc > 8 && N * (kc + 4) > budget) kc /= 2;
+  return kc;
+}
+// largest power-of-two K chunk (>= 8) such that chunk*ld_kn(N) (B_KN) fits `budget` floats
+__host__ __device__ constexpr int kc_kn(int N, int K, int budget) {
+  int kc = K;
+  while (kc > 8 && kc * ld_kn(N) > budget) kc /= 2;
+  return kc;
+}
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int SW_BUDGET = 6144;    // floats of weight staging per CTA at most (24 KB)
+
+// copy `rows` rows of `cols` floats (cols % 4 == 0) from a dense global block to padded smem rows (float4)
+__device__ __forceinline__ void copy_rows_g2s(float* dst, int ldd, const float* __restrict__ src, int rows, int cols) {
+  const int c4n = cols >> 2;
+  for (int i = threadIdx.x; i < rows * c4n; i += RL_NT) {
+    const int r = i / c4n, c4 = i % c4n;
+    *reinterpret_cast<float4*>(dst + r * ldd + 4 * c4) = __ldg(reinterpret_cast<const float4*>(src + r * cols) + c4);
+  }
+}
+__device__ __forceinline__ void copy_rows_s2g(float* __restrict__ dst, const float* src, int lds, int rows, int cols) {
+  const int c4n = cols >> 2;
+  for (int i = threadIdx.x; i < rows * c4n; i += RL_NT) {
+    const int r = i / c4n, c4 = i % c4n;
+    reinterpret_cast<float4*>(dst + r * cols)[c4] = *reinterpret_cast<const float4*>(src + r * lds + 4 * c4);
+  }
+}
+// stage a weight block: dst[r*ldd + c] = W[(r0+r)*ldw + c0 + c], r < R, c < Cc (Cc, c0, ldw, ldd % 4 == 0), float4
+__device__ __forceinline__ void stage_w4(float* dst, int ldd, const float* __restrict__ W, int ldw, int r0, int R,
+                                         int c0, int Cc) {
+  const int c4n = Cc >> 2;
+  for (int i = threadIdx.x; i < R * c4n; i += RL_NT) {
+    const int r = i / c4n, c4 = i % c4n;
+    *reinterpret_cast<float4*>(dst + r * ldd + 4 * c4) =
+        __ldg(reinterpret_cast<const float4*>(W + (size_t)(r0 + r) * ldw + c0) + c4);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight streaming for the fused block kernels: the weight matrix stays in global memory (L2-resident, 4.3 MB
+// for the whole network) and is pulled through a 2-stage cp.async ring in K chunks while the previous chunk is
+// being contracted on the tensor cores.
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async16_zfill(float* smem_dst, const float* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int nbytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(nbytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int NPEND>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND)); }
+
+constexpr int STAGE_BUDGET = 6144;   // floats per pipeline stage (24 KB)
+
+template <int N, int K, int BL>
+struct WStream {
+  static constexpr int KC = (BL == B_NK) ? kc_nk(N, K, STAGE_BUDGET) : kc_kn(N, K, STAGE_BUDGET);
+  static constexpr int LD = (BL == B_NK) ? KC + 4 : ld_kn(N);
+  static constexpr int STAGE = (BL == B_NK) ? N * LD : KC * LD;     // floats per stage
+  static constexpr int FLOATS = 2 * STAGE;
+  static constexpr int NCHUNK = K / KC;
+  static_assert(K % KC == 0 && KC % 8 == 0, "WStream: chunking");
+
+  // B_NK: W(n, k) = (n < n_split ? W0[n*ldw + k] : W1[(n-n_split)*ldw + k])     (y = x W^T, W = [N][K])
+  // B_KN: W(k, n) = W0[k*ldw + n]                                                (dx = dy W,  W = [K][N])
+  __device__ static __forceinline__ void issue(float* dst, const float* __restrict__ W0, int n_split,
+                                               const float* __restrict__ W1, int ldw, int k0) {
+    if (BL == B_NK) {
+      constexpr int V = KC / 4;
+      for (int i = threadIdx.x; i < N * V; i += RL_NT) {
+        const int n = i / V, c = (i % V) * 4;
+        const float* row = (n < n_split) ? W0 + (size_t)n * ldw : W1 + (size_t)(n - n_split) * ldw;
+        cp_async16(dst + n * LD + c, row + k0 + c);
+      }
+    } else {
+      constexpr int V = N / 4;
+      for (int i = threadIdx.x; i < KC * V; i += RL_NT) {
+        const int r = i / V, c = (i % V) * 4;
+        cp_async16(dst + r * LD + c, W0 + (size_t)(k0 + r) * ldw + c);
+      }
+    }
+    cp_async_commit();
+  }
+
+  // acc += A[:, 0:K] * W      (A in smem, A_MK with stride lda; sw holds FLOATS floats)
+  template <class Acc>
+  __device__ static __forceinline__ void run(Acc& acc, const float* A, int lda, float* sw,
+                                             const float* __restrict__ W0, int n_split,
+                                             const float* __restrict__ W1, int ldw) {
+    issue(sw, W0, n_split, W1, ldw, 0);
+#pragma unroll 1
+    for (int c = 0; c < NCHUNK; ++c) {
+      if (c + 1 < NCHUNK) {
+        issue(sw + ((c + 1) & 1) * STAGE, W0, n_split, W1, ldw, (c + 1) * KC);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      acc.template mac<A_MK, BL>(A + c * KC, lda, sw + (c & 1) * STAGE, LD, KC);
+      __syncthreads();
+    }
+  }
+};
+
 // generic weight-gradient GEMM launcher (wgrad.cu):
 //   dW[n*K + k] += sum_m dY[m*ldy + n] * X[m*ldx + k]      n < N, k < K, m < M
 //   db[n]       += sum_m dY[m*ldy + n]                     (db may be NULL)
 int rl_launch_wgrad(const float* dY, int ldy, const float* X, int ldx, int M, int N, int K, float* dW, float* db,
                     cudaStream_t st);
+// grouped form: all weight matrices of one half-block in one launch (tensor-core path when every dim % 32 == 0)
+struct RlWgradDesc {
+  const float* dY; int ldy; const float* X; int ldx; int N, K; float* dW; float* db;
+};
+int rl_launch_wgrad_group(const RlWgradDesc* d, int n, int M, cudaStream_t st);

@@ -12,20 +12,24 @@
 namespace {
 
 template <int C>
+__host__ __device__ constexpr int ffn_fwd_swf() {
+  return cmax(WStream<4 * C, C, B_NK>::FLOATS, WStream<C, 4 * C, B_NK>::FLOATS);
+}
+template <int C>
 size_t ffn_fwd_smem(int L) {
-  return sizeof(float) * ((size_t)L * lda_of<C>() + (size_t)L * (4 * C + 1) + SW_FLOATS + (size_t)L + 64);
+  return sizeof(float) * ((size_t)L * ld_mk(C) + (size_t)L * ld_mk(4 * C) + ffn_fwd_swf<C>() + (size_t)L + 64);
 }
 
 template <int C, int WIN>
 __global__ void __launch_bounds__(RL_NT) ffn_fwd_kernel(const rl_ffn_fwd_args a) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int LDA = lda_of<C>();
-  constexpr int HC = 4 * C, LDH = HC + 1;
-  const int L = a.L;
+  constexpr int L = 2048 * WIN / C;
+  constexpr int LDC = ld_mk(C);
+  constexpr int HC = 4 * C, LDH = ld_mk(HC);
   float* su = smem;
-  float* sh = su + L * LDA;
+  float* sh = su + L * LDC;
   float* sw = sh + L * LDH;
-  float* sfir = sw + SW_FLOATS;
+  float* sfir = sw + ffn_fwd_swf<C>();
   const int tid = threadIdx.x;
   const size_t woff = (size_t)blockIdx.x * L * C;
   const float* xw = a.x + woff;
@@ -36,23 +40,17 @@ __global__ void __launch_bounds__(RL_NT) ffn_fwd_kernel(const rl_ffn_fwd_args a)
     const float* lb = a.ln_b;
     ln_forward_rows<C>(
         L, [&](int t, int c) { return __ldg(xw + t * C + c); },
-        [&](int t, int c, float zh) { su[t * LDA + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c)); });
+        [&](int t, int c, float zh) { su[t * LDC + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c)); });
   } else {
-    for (int i = tid; i < L * C; i += RL_NT) su[(i / C) * LDA + (i % C)] = __ldg(xw + i);
+    copy_rows_g2s(su, LDC, xw, L, C);
   }
   __syncthreads();
 
   // 2. h = u W1^T + b1 (N = 4C, K = C);  g1 = GELU(h) -> sh
   {
-    TileAcc<4 * WIN, 8> acc;
-    acc.init(L, HC);
-    const int KC = min(C, pow2_floor(SW_FLOATS / LDH));
-    for (int k0 = 0; k0 < C; k0 += KC) {
-      stage_wT(sw, LDH, a.w1, C, 0, HC, k0, KC);
-      __syncthreads();
-      acc.mac(su + k0, LDA, 1, sw, LDH, KC);
-      __syncthreads();
-    }
+    MmaTile<L, HC> acc;
+    acc.init();
+    WStream<HC, C, B_NK>::run(acc, su, LDC, sw, a.w1, HC, nullptr, C);
     const float* b1 = a.b1;
     float* hs = a.h ? a.h + (size_t)blockIdx.x * L * HC : nullptr;
     acc.epilogue([&](int t, int n, float v) {
@@ -94,16 +92,9 @@ __global__ void __launch_bounds__(RL_NT) ffn_fwd_kernel(const rl_ffn_fwd_args a)
 
   // 4. y = x + g2 W2^T + b2 (N = C, K = 4C)
   {
-    TileAcc<4 * WIN, 2> acc;
-    acc.init(L, C);
-    const int ldd = C + 1;
-    const int KC = min(HC, pow2_floor(SW_FLOATS / ldd));
-    for (int k0 = 0; k0 < HC; k0 += KC) {
-      stage_wT(sw, ldd, a.w2, HC, 0, C, k0, KC);
-      __syncthreads();
-      acc.mac(sh + k0, LDH, 1, sw, ldd, KC);
-      __syncthreads();
-    }
+    MmaTile<L, C> acc;
+    acc.init();
+    WStream<C, HC, B_NK>::run(acc, sh, LDH, sw, a.w2, C, nullptr, HC);
     const float* b2 = a.b2;
     const float* ex = a.extra ? a.extra + woff : nullptr;
     float* yw = a.y + woff;
@@ -118,24 +109,31 @@ __global__ void __launch_bounds__(RL_NT) ffn_fwd_kernel(const rl_ffn_fwd_args a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Backward.  DW = depthwise mode (needs GELU(h) of the neighbouring tokens, so it keeps the L x 4C g1 tile in
+// shared memory); the shipped partial / plain modes recompute everything they need per element in the
+// epilogue of the dg2 GEMM from the saved pre-activation h (one erf shared by GELU and GELU').
 template <int C>
-size_t ffn_bwd_smem(int L) {
-  return sizeof(float) * (2 * (size_t)L * lda_of<C>() + 2 * (size_t)L * (4 * C + 1) + SW_FLOATS + 3 * (size_t)L +
-                          2 * C + 64);
+__host__ __device__ constexpr int ffn_bwd_swf() {
+  return cmax(WStream<4 * C, C, B_KN>::FLOATS, WStream<C, 4 * C, B_KN>::FLOATS);
+}
+template <int C>
+size_t ffn_bwd_smem(int L, bool dw) {
+  return sizeof(float) * (2 * (size_t)L * ld_mk(C) + (dw ? 2 : 1) * (size_t)L * ld_mk(4 * C) + ffn_bwd_swf<C>() +
+                          3 * (size_t)L + 2 * C + 64);
 }
 
-template <int C, int WIN>
+template <int C, int WIN, bool DW>
 __global__ void __launch_bounds__(RL_NT) ffn_bwd_kernel(const rl_ffn_bwd_args a) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int LDA = lda_of<C>();
-  constexpr int HC = 4 * C, LDH = HC + 1;
-  const int L = a.L;
+  constexpr int L = 2048 * WIN / C;
+  constexpr int LDC = ld_mk(C);
+  constexpr int HC = 4 * C, LDH = ld_mk(HC);
   float* sg = smem;                       // dL/dy, A operand
-  float* su = sg + L * LDA;               // du (LN2 output gradient)
-  float* sh = su + L * LDA;               // g1 = GELU(h)
-  float* sd = sh + L * LDH;               // df / dh
-  float* sw = sd + L * LDH;
-  float* sg10 = sw + SW_FLOATS;           // g1[:,0]
+  float* su = sg + L * LDC;               // du (LN2 output gradient)
+  float* sd = su + L * LDC;               // df / dh
+  float* sh = sd + L * LDH;               // g1 = GELU(h), depthwise mode only
+  float* sw = sh + (DW ? L * LDH : 0);
+  float* sg10 = sw + ffn_bwd_swf<C>();    // g1[:,0]
   float* sf0 = sg10 + L;                  // fir(g1[:,0])
   float* sdf0 = sf0 + L;                  // df[:,0]
   float* s_gb = sdf0 + L;
@@ -146,77 +144,74 @@ __global__ void __launch_bounds__(RL_NT) ffn_bwd_kernel(const rl_ffn_bwd_args a)
   const float* gw = a.g + woff;
   const float* xw = a.x + woff;
   const float* hw = a.h + hoff;
+  float* g2w = a.g2 + hoff;
+  float* dhw = a.dh + hoff;
   const int mode = a.le_mode;
 
-  // 1. g -> sg, g1 = GELU(h) -> sh
-  for (int i = tid; i < L * C; i += RL_NT) sg[(i / C) * LDA + (i % C)] = __ldg(gw + i);
-  for (int i = tid; i < L * HC; i += RL_NT) sh[(i / HC) * LDH + (i % HC)] = gelu_f(__ldg(hw + i));
+  // 1. g -> sg; the pieces of g1 = GELU(h) that cross tokens
+  copy_rows_g2s(sg, LDC, gw, L, C);
   for (int i = tid; i < 2 * C; i += RL_NT) s_gb[i] = 0.f;
-  __syncthreads();
-
-  // 2. second-GELU input f and g2 = GELU(f) (written to scratch for the fc2 weight gradient)
   float lw0 = 0.f, lw1 = 0.f, lw2 = 0.f;
-  if (mode == RL_LE_PARTIAL) {
+  if (DW) {
+    for (int i = tid; i < L * HC; i += RL_NT) sh[(i / HC) * LDH + (i % HC)] = gelu_f(__ldg(hw + i));
+  } else if (mode == RL_LE_PARTIAL) {
     lw0 = __ldg(a.lew); lw1 = __ldg(a.lew + 1); lw2 = __ldg(a.lew + 2);
-    for (int t = tid; t < L; t += RL_NT) {
-      const float p = (t > 0) ? sh[(t - 1) * LDH] : 0.f;
-      const float n = (t + 1 < L) ? sh[(t + 1) * LDH] : 0.f;
-      sg10[t] = sh[t * LDH];
-      sf0[t] = lw0 * p + lw1 * sh[t * LDH] + lw2 * n;
-    }
+    for (int t = tid; t < L; t += RL_NT) sg10[t] = gelu_f(__ldg(hw + t * HC));
     __syncthreads();
+    for (int t = tid; t < L; t += RL_NT) {
+      const float p = (t > 0) ? sg10[t - 1] : 0.f;
+      const float n = (t + 1 < L) ? sg10[t + 1] : 0.f;
+      sf0[t] = lw0 * p + lw1 * sg10[t] + lw2 * n;
+    }
   }
-  {
-    float* g2w = a.g2 + hoff;
+  __syncthreads();
+  if (DW) {   // g2 = GELU(fir(g1)) for the fc2 weight gradient
     for (int i = tid; i < L * HC; i += RL_NT) {
       const int t = i / HC, n = i % HC;
-      float v = sh[t * LDH + n];
-      if (mode == RL_LE_PARTIAL) {
-        v = gelu_f(n == 0 ? sf0[t] : v);
-      } else if (mode == RL_LE_DEPTHWISE) {
-        const float p = (t > 0) ? sh[(t - 1) * LDH + n] : 0.f;
-        const float nx = (t + 1 < L) ? sh[(t + 1) * LDH + n] : 0.f;
-        v = gelu_f(__ldg(a.lew + 3 * n) * p + __ldg(a.lew + 3 * n + 1) * v + __ldg(a.lew + 3 * n + 2) * nx);
-      }
-      g2w[i] = v;
+      const float p = (t > 0) ? sh[(t - 1) * LDH + n] : 0.f;
+      const float nx = (t + 1 < L) ? sh[(t + 1) * LDH + n] : 0.f;
+      g2w[i] = gelu_f(__ldg(a.lew + 3 * n) * p + __ldg(a.lew + 3 * n + 1) * sh[t * LDH + n] +
+                      __ldg(a.lew + 3 * n + 2) * nx);
     }
   }
 
-  // 3. dg2 = g W2 (N = 4C, K = C; B(k,n) = W2[k][n] natural layout), then through GELU'/FIR^T/GELU'
+  // 2. dg2 = g W2 (N = 4C, K = C; B(k,n) = W2[k][n] natural layout), then through GELU' / FIR^T / GELU'
   {
-    TileAcc<4 * WIN, 8> acc;
-    acc.init(L, HC);
-    const int KC = min(C, pow2_floor(SW_FLOATS / LDH));
-    for (int k0 = 0; k0 < C; k0 += KC) {
-      stage_w(sw, LDH, a.w2, HC, k0, KC, 0, HC);
-      __syncthreads();
-      acc.mac(sg + k0, LDA, 1, sw, LDH, KC);
-      __syncthreads();
-    }
-    float* dhw = a.dh + hoff;
+    MmaTile<L, HC> acc;
+    acc.init();
+    WStream<HC, C, B_KN>::run(acc, sg, LDC, sw, a.w2, 0, nullptr, HC);
     acc.epilogue([&](int t, int n, float v) {
-      if (mode == RL_LE_NONE) {
-        const float dh = v * gelu_grad_f(__ldg(hw + t * HC + n));
-        sd[t * LDH + n] = dh;
-        dhw[t * HC + n] = dh;
-      } else if (mode == RL_LE_PARTIAL) {
-        if (n == 0) {
-          sdf0[t] = v * gelu_grad_f(sf0[t]);
-        } else {
-          const float dh = v * gelu_grad_f(sh[t * LDH + n]) * gelu_grad_f(__ldg(hw + t * HC + n));
-          sd[t * LDH + n] = dh;
-          dhw[t * HC + n] = dh;
-        }
-      } else {
+      if (DW) {
         const float g1 = sh[t * LDH + n];
         const float p = (t > 0) ? sh[(t - 1) * LDH + n] : 0.f;
         const float nx = (t + 1 < L) ? sh[(t + 1) * LDH + n] : 0.f;
         const float f = __ldg(a.lew + 3 * n) * p + __ldg(a.lew + 3 * n + 1) * g1 + __ldg(a.lew + 3 * n + 2) * nx;
         sd[t * LDH + n] = v * gelu_grad_f(f);          // df, finished below
+      } else {
+        float g1, d1;
+        gelu_both(__ldg(hw + t * HC + n), g1, d1);
+        if (mode == RL_LE_NONE) {
+          g2w[t * HC + n] = g1;
+          const float dh = v * d1;
+          sd[t * LDH + n] = dh;
+          dhw[t * HC + n] = dh;
+        } else if (n == 0) {                           // partial, convolved channel: finish after the FIR adjoint
+          float g2, d2;
+          gelu_both(sf0[t], g2, d2);
+          g2w[t * HC] = g2;
+          sdf0[t] = v * d2;
+        } else {                                       // partial, untouched channel: f == g1
+          float g2, d2;
+          gelu_both(g1, g2, d2);
+          g2w[t * HC + n] = g2;
+          const float dh = v * d2 * d1;
+          sd[t * LDH + n] = dh;
+          dhw[t * HC + n] = dh;
+        }
       }
     });
     __syncthreads();
-    if (mode == RL_LE_PARTIAL) {
+    if (!DW && mode == RL_LE_PARTIAL) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f;
       for (int t = tid; t < L; t += RL_NT) {
         const float d = sdf0[t];
@@ -241,7 +236,7 @@ __global__ void __launch_bounds__(RL_NT) ffn_bwd_kernel(const rl_ffn_bwd_args a)
         }
       }
       __syncthreads();
-    } else if (mode == RL_LE_DEPTHWISE) {
+    } else if (DW) {
       for (int c = tid; c < HC; c += RL_NT) {
         const float w0 = __ldg(a.lew + 3 * c), w1 = __ldg(a.lew + 3 * c + 1), w2 = __ldg(a.lew + 3 * c + 2);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -268,23 +263,16 @@ __global__ void __launch_bounds__(RL_NT) ffn_bwd_kernel(const rl_ffn_bwd_args a)
     }
   }
 
-  // 4. du = dh W1 (N = C, K = 4C; B(k,n) = W1[k][n] natural layout)
+  // 3. du = dh W1 (N = C, K = 4C; B(k,n) = W1[k][n] natural layout)
   {
-    TileAcc<4 * WIN, 2> acc;
-    acc.init(L, C);
-    const int ldd = C + 1;
-    const int KC = min(HC, pow2_floor(SW_FLOATS / ldd));
-    for (int k0 = 0; k0 < HC; k0 += KC) {
-      stage_w(sw, ldd, a.w1, C, k0, KC, 0, C);
-      __syncthreads();
-      acc.mac(sd + k0, LDH, 1, sw, ldd, KC);
-      __syncthreads();
-    }
-    acc.epilogue([&](int t, int n, float v) { su[t * LDA + n] = v; });
+    MmaTile<L, C> acc;
+    acc.init();
+    WStream<C, HC, B_KN>::run(acc, sd, LDH, sw, a.w1, 0, nullptr, C);
+    acc.epilogue([&](int t, int n, float v) { su[t * LDC + n] = v; });
   }
   __syncthreads();
 
-  // 5. LN2 backward + residual
+  // 4. LN2 backward + residual
   float* dxw = a.dx + woff;
   float* uw = a.u + woff;
   const bool resid = a.flags & RL_F_RESIDUAL;
@@ -292,9 +280,9 @@ __global__ void __launch_bounds__(RL_NT) ffn_bwd_kernel(const rl_ffn_bwd_args a)
     const float* lw = a.ln_w;
     const float* lb = a.ln_b;
     ln_backward_rows<C>(
-        L, lw, s_gb, [&](int t, int c) { return __ldg(xw + t * C + c); }, [&](int t, int c) { return su[t * LDA + c]; },
+        L, lw, s_gb, [&](int t, int c) { return __ldg(xw + t * C + c); }, [&](int t, int c) { return su[t * LDC + c]; },
         [&](int t, int c, float dz, float zh) {
-          dxw[t * C + c] = (resid ? sg[t * LDA + c] : 0.f) + dz;
+          dxw[t * C + c] = (resid ? sg[t * LDC + c] : 0.f) + dz;
           uw[t * C + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c));
         });
     __syncthreads();
@@ -306,7 +294,7 @@ __global__ void __launch_bounds__(RL_NT) ffn_bwd_kernel(const rl_ffn_bwd_args a)
   } else {
     for (int i = tid; i < L * C; i += RL_NT) {
       const int t = i / C, c = i % C;
-      dxw[i] = su[t * LDA + c] + (resid ? sg[t * LDA + c] : 0.f);
+      dxw[i] = su[t * LDC + c] + (resid ? sg[t * LDC + c] : 0.f);
       uw[i] = __ldg(xw + i);
     }
   }
@@ -325,17 +313,19 @@ int launch_fwd(const rl_ffn_fwd_args* a, cudaStream_t st) {
   return rl_check_launch("ffn_fwd_kernel", C);
 }
 
+template <int C, int WIN, bool DW>
+int launch_bwd_one(const rl_ffn_bwd_args* a, cudaStream_t st) {
+  const size_t smem = ffn_bwd_smem<C>(a->L, DW);
+  if (int rc = rl_set_smem(ffn_bwd_kernel<C, WIN, DW>, smem)) return rc;
+  ffn_bwd_kernel<C, WIN, DW><<<a->B, RL_NT, smem, st>>>(*a);
+  return rl_check_launch("ffn_bwd_kernel", C);
+}
+
 template <int C>
 int launch_bwd(const rl_ffn_bwd_args* a, cudaStream_t st) {
-  const size_t smem = ffn_bwd_smem<C>(a->L);
-  if (a->L * C == 2048) {
-    if (int rc = rl_set_smem(ffn_bwd_kernel<C, 1>, smem)) return rc;
-    ffn_bwd_kernel<C, 1><<<a->B, RL_NT, smem, st>>>(*a);
-  } else {
-    if (int rc = rl_set_smem(ffn_bwd_kernel<C, 2>, smem)) return rc;
-    ffn_bwd_kernel<C, 2><<<a->B, RL_NT, smem, st>>>(*a);
-  }
-  return rl_check_launch("ffn_bwd_kernel", C);
+  const bool dw = a->le_mode == RL_LE_DEPTHWISE;
+  if (a->L * C == 2048) return dw ? launch_bwd_one<C, 1, true>(a, st) : launch_bwd_one<C, 1, false>(a, st);
+  return dw ? launch_bwd_one<C, 2, true>(a, st) : launch_bwd_one<C, 2, false>(a, st);
 }
 
 int check_shape(int B, int L, int C, int le) {
@@ -384,7 +374,7 @@ extern "C" int ralenet_ffn_bwd(const rl_ffn_bwd_args* a, void* stream) {
   }
   if (rc) return rc;
   const int M = a->B * a->L, C = a->C;
-  if ((rc = rl_launch_wgrad(a->g, C, a->g2, 4 * C, M, C, 4 * C, a->d_w2, a->d_b2, st))) return rc;
-  if ((rc = rl_launch_wgrad(a->dh, 4 * C, a->u, C, M, 4 * C, C, a->d_w1, a->d_b1, st))) return rc;
-  return RL_OK;
+  const RlWgradDesc d[2] = {{a->g, C, a->g2, 4 * C, C, 4 * C, a->d_w2, a->d_b2},
+                            {a->dh, 4 * C, a->u, C, 4 * C, C, a->d_w1, a->d_b1}};
+  return rl_launch_wgrad_group(d, 2, M, st);
 }

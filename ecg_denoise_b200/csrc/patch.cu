@@ -16,14 +16,18 @@ __device__ __forceinline__ int src_index(int mode, int L, int C, int Cn, int r, 
 }
 
 template <int CN>
-size_t patch_smem(int rows) { return sizeof(float) * (2 * (size_t)rows * lda_of<CN>() + SW_FLOATS + 2 * CN + 64); }
+__host__ __device__ constexpr int patch_swf() {
+  return cmax(WStream<CN, CN, B_NK>::FLOATS, WStream<CN, CN, B_KN>::FLOATS);
+}
+template <int CN>
+size_t patch_smem(int rows) { return sizeof(float) * (2 * (size_t)rows * ld_mk(CN) + patch_swf<CN>() + 2 * CN + 64); }
 
 template <int CN, int WIN>
 __global__ void __launch_bounds__(RL_NT) patch_fwd_kernel(const rl_patch_fwd_args a) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int LDA = lda_of<CN>();
+  constexpr int LDA = ld_mk(CN);
+  constexpr int rows = 2048 * WIN / CN;
   const int L = a.L, C = a.C, mode = a.mode;
-  const int rows = L * C / CN;
   float* su = smem;
   float* sw = su + 2 * rows * LDA;
   const size_t woff = (size_t)blockIdx.x * L * C;
@@ -41,16 +45,9 @@ __global__ void __launch_bounds__(RL_NT) patch_fwd_kernel(const rl_patch_fwd_arg
         });
   }
   __syncthreads();
-  TileAcc<4 * WIN, 2> acc;
-  acc.init(rows, CN);
-  const int ldd = CN + 1;
-  const int KC = min(CN, pow2_floor(SW_FLOATS / ldd));
-  for (int k0 = 0; k0 < CN; k0 += KC) {
-    stage_wT(sw, ldd, a.w, CN, 0, CN, k0, KC);
-    __syncthreads();
-    acc.mac(su + k0, LDA, 1, sw, ldd, KC);
-    __syncthreads();
-  }
+  MmaTile<rows, CN> acc;
+  acc.init();
+  WStream<CN, CN, B_NK>::run(acc, su, LDA, sw, a.w, CN, nullptr, CN);
   const float* sk = a.skip ? a.skip + woff : nullptr;
   float* yw = a.y + woff;
   acc.epilogue([&](int r, int n, float v) {
@@ -62,13 +59,13 @@ __global__ void __launch_bounds__(RL_NT) patch_fwd_kernel(const rl_patch_fwd_arg
 template <int CN, int WIN>
 __global__ void __launch_bounds__(RL_NT) patch_bwd_kernel(const rl_patch_bwd_args a, float* __restrict__ gsum) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int LDA = lda_of<CN>();
+  constexpr int LDA = ld_mk(CN);
+  constexpr int rows = 2048 * WIN / CN;
   const int L = a.L, C = a.C, mode = a.mode;
-  const int rows = L * C / CN;
   float* sg = smem;
   float* su = sg + rows * LDA;
   float* sw = su + rows * LDA;
-  float* s_gb = sw + SW_FLOATS;
+  float* s_gb = sw + patch_swf<CN>();
   const int tid = threadIdx.x;
   const size_t woff = (size_t)blockIdx.x * L * C;
   const float* gw = a.g + woff;
@@ -85,16 +82,9 @@ __global__ void __launch_bounds__(RL_NT) patch_bwd_kernel(const rl_patch_bwd_arg
   for (int i = tid; i < 2 * CN; i += RL_NT) s_gb[i] = 0.f;
   __syncthreads();
   {
-    TileAcc<4 * WIN, 2> acc;
-    acc.init(rows, CN);
-    const int ldd = CN + 1;
-    const int KC = min(CN, pow2_floor(SW_FLOATS / ldd));
-    for (int k0 = 0; k0 < CN; k0 += KC) {
-      stage_w(sw, ldd, a.w, CN, k0, KC, 0, CN);
-      __syncthreads();
-      acc.mac(sg + k0, LDA, 1, sw, ldd, KC);
-      __syncthreads();
-    }
+    MmaTile<rows, CN> acc;
+    acc.init();
+    WStream<CN, CN, B_KN>::run(acc, sg, LDA, sw, a.w, 0, nullptr, CN);
     acc.epilogue([&](int r, int n, float v) { su[r * LDA + n] = v; });
   }
   __syncthreads();
@@ -186,5 +176,6 @@ extern "C" int ralenet_patch_bwd(const rl_patch_bwd_args* a, void* stream) {
   }
   if (rc) return rc;
   const int M = a->B * (a->L * a->C / CN);
-  return rl_launch_wgrad(a->g2 ? a->gsum : a->g, CN, a->u, CN, M, CN, CN, a->d_w, nullptr, st);
+  const RlWgradDesc d[1] = {{a->g2 ? a->gsum : a->g, CN, a->u, CN, CN, CN, a->d_w, nullptr}};
+  return rl_launch_wgrad_group(d, 1, M, st);
 }

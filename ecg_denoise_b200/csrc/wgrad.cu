@@ -105,6 +105,144 @@ inline int pick_tile(int n) {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// Grouped tensor-core weight gradients: up to 4 (dY, X) -> dW problems that share the token dimension M
+// (all weight matrices of one attention / feed-forward half) in ONE launch.  Each CTA owns a T x T tile of
+// one dW and a slice of tokens; the token slice is streamed through a 2-stage cp.async pipeline and
+// contracted with 3xTF32 mma.sync (A = dY^T in A_KM layout, B = X in B_KN layout); fp32 red.global at the end.
+namespace {
+
+struct WgProblem {
+  const float* dY; const float* X; float* dW; float* db;
+  int ldy, ldx, N, K, tile_begin, tiles_k;
+};
+struct WgGroup {
+  WgProblem p[4];
+  int nprob, M, MC;
+};
+
+constexpr int WG_MS = 64;   // tokens per pipeline stage
+
+template <int T>
+__global__ void __launch_bounds__(RL_NT) wgrad_group_kernel(const WgGroup grp) {
+  constexpr int LD = T + 8;                     // % 32 in {8, 24}: conflict-free A_KM / B_KN fragment loads
+  extern __shared__ __align__(16) float smem[];
+  float* sA = smem;                             // [2][WG_MS][LD]  dY tile
+  float* sB = smem + 2 * WG_MS * LD;            // [2][WG_MS][LD]  X tile
+  const int tid = threadIdx.x;
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (i < grp.nprob && (int)blockIdx.x >= grp.p[i].tile_begin) pi = i;
+  const WgProblem& P = grp.p[pi];
+  const int tile = blockIdx.x - P.tile_begin;
+  const int n_base = (tile / P.tiles_k) * T, k_base = (tile % P.tiles_k) * T;
+  const int m_begin = blockIdx.y * grp.MC;
+  const int m_end = min(grp.M, m_begin + grp.MC);
+  const int nst = (m_end - m_begin + WG_MS - 1) / WG_MS;
+  const float* gA = P.dY + n_base;
+  const float* gB = P.X + k_base;
+  const int ldy = P.ldy, ldx = P.ldx;
+
+  auto issue = [&](int st) {
+    const int m0 = m_begin + st * WG_MS;
+    float* dA = sA + (st & 1) * WG_MS * LD;
+    float* dB = sB + (st & 1) * WG_MS * LD;
+    constexpr int V = T / 4;                    // float4 per row
+    for (int i = tid; i < WG_MS * V; i += RL_NT) {
+      const int r = i / V, c = (i % V) * 4;
+      const bool ok = (m0 + r) < m_end;
+      const size_t row = ok ? (size_t)(m0 + r) : (size_t)m_begin;
+      cp_async16_zfill(dA + r * LD + c, gA + row * ldy + c, ok);
+      cp_async16_zfill(dB + r * LD + c, gB + row * ldx + c, ok);
+    }
+    cp_async_commit();
+  };
+
+  MmaTile<T, T> acc;
+  acc.init();
+  float bacc = 0.f;
+  const bool do_bias = (P.db != nullptr) && (k_base == 0);
+  if (nst > 0) issue(0);
+  for (int st = 0; st < nst; ++st) {
+    if (st + 1 < nst) {
+      issue(st + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* cA = sA + (st & 1) * WG_MS * LD;
+    const float* cB = sB + (st & 1) * WG_MS * LD;
+    acc.template mac<A_KM, B_KN>(cA, LD, cB, LD, WG_MS);
+    if (do_bias && tid < T) {
+#pragma unroll 8
+      for (int r = 0; r < WG_MS; ++r) bacc += cA[r * LD + tid];
+    }
+    __syncthreads();
+  }
+  float* dW = P.dW;
+  const int K = P.K;
+  acc.epilogue([&](int n, int k, float v) { atomicAdd(dW + (size_t)(n_base + n) * K + k_base + k, v); });
+  if (do_bias && tid < T) atomicAdd(P.db + n_base + tid, bacc);
+}
+
+template <int T>
+int launch_group(WgGroup& g, int total_tiles, cudaStream_t st) {
+  int splits = (444 + total_tiles - 1) / total_tiles;            // ~3 CTAs per SM overall
+  const int max_splits = (g.M + 2 * WG_MS - 1) / (2 * WG_MS);    // at least 2 pipeline stages per CTA
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int MC = (g.M + splits - 1) / splits;
+  MC = ((MC + WG_MS - 1) / WG_MS) * WG_MS;
+  splits = (g.M + MC - 1) / MC;
+  g.MC = MC;
+  const size_t smem = sizeof(float) * 4 * WG_MS * (T + 8);
+  if (int rc = rl_set_smem(wgrad_group_kernel<T>, smem)) return rc;
+  dim3 grid(total_tiles, splits);
+  wgrad_group_kernel<T><<<grid, RL_NT, smem, st>>>(g);
+  return rl_check_launch("wgrad_group_kernel", T, total_tiles);
+}
+
+}  // namespace
+
+// up to 4 problems sharing M; dims must all be multiples of 32 for the tensor-core path, otherwise the
+// problems are launched one by one on the FFMA kernel.
+int rl_launch_wgrad_group(const RlWgradDesc* d, int n, int M, cudaStream_t st) {
+  int cnt = 0, mind = 1 << 30;
+  bool aligned = true;
+  for (int i = 0; i < n; ++i) {
+    if (!d[i].dW) continue;
+    ++cnt;
+    mind = min(mind, min(d[i].N, d[i].K));
+    aligned = aligned && (d[i].N % 32 == 0) && (d[i].K % 32 == 0) && (d[i].ldy % 4 == 0) && (d[i].ldx % 4 == 0) &&
+              ((uintptr_t)d[i].dY % 16 == 0) && ((uintptr_t)d[i].X % 16 == 0);
+  }
+  if (cnt == 0) return RL_OK;
+  if (!aligned || cnt > 4) {
+    for (int i = 0; i < n; ++i)
+      if (int rc = rl_launch_wgrad(d[i].dY, d[i].ldy, d[i].X, d[i].ldx, M, d[i].N, d[i].K, d[i].dW, d[i].db, st))
+        return rc;
+    return RL_OK;
+  }
+  const int T = (mind % 64 == 0) ? 64 : 32;
+  WgGroup g;
+  g.nprob = 0;
+  g.M = M;
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!d[i].dW) continue;
+    WgProblem& p = g.p[g.nprob++];
+    p.dY = d[i].dY; p.X = d[i].X; p.dW = d[i].dW; p.db = d[i].db;
+    p.ldy = d[i].ldy; p.ldx = d[i].ldx; p.N = d[i].N; p.K = d[i].K;
+    p.tile_begin = tiles;
+    p.tiles_k = d[i].K / T;
+    tiles += (d[i].N / T) * (d[i].K / T);
+  }
+  for (int i = g.nprob; i < 4; ++i) g.p[i] = g.p[0];
+  return T == 64 ? launch_group<64>(g, tiles, st) : launch_group<32>(g, tiles, st);
+}
+
 int rl_launch_wgrad(const float* dY, int ldy, const float* X, int ldx, int M, int N, int K, float* dW, float* db,
                     cudaStream_t st) {
   if (dW == nullptr) return RL_OK;

@@ -350,7 +350,11 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_base,
         }
         print(json.dumps(line))
+    trainer.close()
+    eager.close()
     if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -319,34 +319,55 @@ class FusedTrainer:
         else:
             self.mask = None
 
-    def _step_impl(self, x, target):
+    def _pieces(self, x, target):
+        """the step as an ordered list of ("compute" | "collective", fn) pieces; collectives only when world > 1.
+        Results are left in self._res = (loss, rmse, snr, out)."""
         plan, ops = self.plan, self.ops
         B, _, L0 = x.shape
-        self.net.train()
-        ws = self._ws
-        cfg = plan.cfg(B, L0, True, True, ws)
-        st = ctypes.c_void_p(_stream())
-        out = self._out
-        plan.flat_grad.zero_()
-        _call("ralenet_net_fwd_stats", ctypes.byref(cfg), ctypes.byref(plan.P), ctypes.c_void_p(x.data_ptr()), st)
-        if self.world > 1:
-            self._allreduce(plan.bn_stats[:17])
-        _call("ralenet_net_fwd", ctypes.byref(cfg), ctypes.byref(plan.P), ctypes.c_void_p(x.data_ptr()),
-              ctypes.c_void_p(out.data_ptr()), st)
-        loss, dout, rmse, snr = ops.mse_loss_metrics(out, target, True, 1.0, out.numel() * self.world)
-        _call("ralenet_net_bwd", ctypes.byref(cfg), ctypes.byref(plan.P), ctypes.byref(plan.G),
-              ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(dout.data_ptr()), st)
-        if self.world > 1:
-            self._allreduce(plan.bn_stats[32:48])
-        _call("ralenet_net_bwd_stem", ctypes.byref(cfg), ctypes.byref(plan.P), ctypes.byref(plan.G),
-              ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(None), st)
-        if self.world > 1:
-            self._allreduce(plan.flat_grad)          # dout already carries 1/global_numel
-            self._allreduce(loss)
-        if self.mask is not None:
-            plan.flat_grad.mul_(self.mask)
-        ops.adam_flat(plan.flat, plan.flat_grad, self.m, self.v, self.step_dev, self.lr, self.betas, self.eps, 1.0)
-        return loss, rmse, snr, out
+        ws, out = self._ws, self._out
+        xp = ctypes.c_void_p(x.data_ptr())
+
+        def cfg():
+            return plan.cfg(B, L0, True, True, ws)
+
+        def st():
+            return ctypes.c_void_p(_stream())
+
+        def seg_a():
+            self.net.train()
+            plan.flat_grad.zero_()
+            _call("ralenet_net_fwd_stats", ctypes.byref(cfg()), ctypes.byref(plan.P), xp, st())
+
+        def seg_b():
+            c = cfg()
+            _call("ralenet_net_fwd", ctypes.byref(c), ctypes.byref(plan.P), xp, ctypes.c_void_p(out.data_ptr()), st())
+            loss, dout, rmse, snr = ops.mse_loss_metrics(out, target, True, 1.0, out.numel() * self.world)
+            _call("ralenet_net_bwd", ctypes.byref(c), ctypes.byref(plan.P), ctypes.byref(plan.G), xp,
+                  ctypes.c_void_p(dout.data_ptr()), st())
+            self._res = (loss, rmse, snr, out)
+            self._dout = dout
+
+        def seg_c():
+            _call("ralenet_net_bwd_stem", ctypes.byref(cfg()), ctypes.byref(plan.P), ctypes.byref(plan.G), xp,
+                  ctypes.c_void_p(None), st())
+
+        def seg_d():
+            if self.mask is not None:
+                plan.flat_grad.mul_(self.mask)
+            ops.adam_flat(plan.flat, plan.flat_grad, self.m, self.v, self.step_dev, self.lr, self.betas, self.eps, 1.0)
+
+        if self.world == 1:
+            return [("compute", lambda: (seg_a(), seg_b(), seg_c(), seg_d()))]
+        return [("compute", seg_a), ("collective", lambda: self._allreduce(plan.bn_stats[:17])),
+                ("compute", seg_b), ("collective", lambda: self._allreduce(plan.bn_stats[32:48])),
+                ("compute", seg_c),
+                ("collective", lambda: (self._allreduce(plan.flat_grad), self._allreduce(self._res[0]))),
+                ("compute", seg_d)]
+
+    def _step_impl(self, x, target):
+        for _, fn in self._pieces(x, target):
+            fn()
+        return self._res
 
     def _prepare(self, shape, device):
         if self._static is not None and tuple(self._static[0].shape) == tuple(shape):
@@ -361,6 +382,8 @@ class FusedTrainer:
         self.graph = None
 
     def _replay(self):
+        """graph mode: every compute piece is captured once into its own CUDA graph (one shared memory pool);
+        NCCL collectives stay outside the graphs and are enqueued between the replays."""
         sx, st_ = self._static
         if self.graph is None:
             # warm up on a side stream (also initialises NCCL communicators), then capture
@@ -372,15 +395,35 @@ class FusedTrainer:
             with torch.cuda.stream(s):
                 self._step_impl(sx, st_)
             torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
             # undo the warm-up step so that capture + replay applies exactly one update per call
             self.plan.flat.copy_(snap[0]); self.m.copy_(snap[1]); self.v.copy_(snap[2]); self.step_dev.copy_(snap[3])
             bn.running_mean.copy_(snap[4]); bn.running_var.copy_(snap[5]); bn.num_batches_tracked.copy_(snap[6])
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._graph_out = self._step_impl(sx, st_)
+            plan = []
+            pool = None
+            for kind, fn in self._pieces(sx, st_):
+                if kind == "collective":
+                    plan.append((None, fn))
+                    continue
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
+                    fn()
+                pool = g.pool()
+                plan.append((g, None))
+            self.graph = plan
+            self._graph_out = self._res
             # capture does not execute: the replay below performs the step
-        self.graph.replay()
+        for g, fn in self.graph:
+            if g is not None:
+                g.replay()
+            else:
+                fn()
         return self._graph_out
+
+    def close(self):
+        """drop the captured graphs (call before destroying the process group)."""
+        self.graph = None
+        self._graph_out = None
 
     def step(self, x: torch.Tensor, target: torch.Tensor):
         """one training step on DEVICE tensors x, target of shape (B, 2, L).  Returns (loss[1], rmse[B], snr[B],

@@ -9,6 +9,8 @@
 // whole window (x, q, k, v) lives in shared memory and the L x L logits are never materialised:
 // each thread owns one (head, query) row and streams the keys with an online softmax.  The R-wave
 // bias is added from its (2W-1) x H table on the central W x W block only.
+#define RL_NT 512        // 16 warps per window: the benchmark batch (256 windows on 148 SMs) needs the parallelism
+#define RL_MINB 2
 #include "common.cuh"
 
 namespace {
@@ -22,7 +24,9 @@ size_t attn_fwd_smem(int L) { return sizeof(float) * (4 * (size_t)L * ld_mk(C) +
 
 // ---------------------------------------------------------------------------------------------
 template <int C, int WIN>
-__global__ void __launch_bounds__(RL_NT) attn_fwd_kernel(const rl_attn_fwd_args a) {
+__global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_kernel(const rl_attn_fwd_args a) {
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   extern __shared__ __align__(16) float smem[];
   constexpr int L = 2048 * WIN / C, H = C / RL_HD;
   constexpr int LDC = ld_mk(C);
@@ -148,7 +152,9 @@ size_t attn_bwd_smem(int L) {
 }
 
 template <int C, int WIN>
-__global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args a) {
+__global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_bwd_args a) {
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   extern __shared__ __align__(16) float smem[];
   constexpr int L = 2048 * WIN / C, H = C / RL_HD;
   constexpr int LDC = ld_mk(C), LC = L * C, LP = L * LDC;
@@ -202,6 +208,10 @@ __global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args 
     sD[item] = d4.x * o4.x + d4.y * o4.y + d4.z * o4.z + d4.w * o4.w;
   }
   __syncthreads();
+
+  constexpr bool FW = (C <= 16);   // narrow stages: weight gradients are accumulated in-CTA (no wgrad launch)
+  if (FW) cta_wgrad<C, C, L>(sdq, LDC, sdk, LDC, a.d_wp, a.d_bp);          // dWp = g^T o,  dbp = sum g
+  if (FW) __syncthreads();
 
   const float qs = 0.5f * RL_LOG2E;
   // 4a. dq: one (head, query) row per thread
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args 
   __syncthreads();
 
   // 5. dqkv scratch [t][dq | dk | dv] for the weight-gradient GEMMs
-  {
+  if (!FW) {
     float* dst = a.dqkv + (size_t)blockIdx.x * 3 * LC;
     constexpr int C4 = C / 4;
     for (int i = tid; i < 3 * L * C4; i += RL_NT) {
@@ -294,7 +304,8 @@ __global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args 
         [&](int t, int c) { return su[t * LDC + c]; },
         [&](int t, int c, float dz, float zh) {
           dxw[t * C + c] = (resid ? __ldg(gw + t * C + c) : 0.f) + sc * dz;
-          uw[t * C + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c));
+          const float u = fmaf(zh, __ldg(lw + c), __ldg(lb + c));
+          if (FW) su[t * LDC + c] = u; else uw[t * C + c] = u;      // du at (t, c) was consumed by this thread
         });
     __syncthreads();
     if (a.d_ln_w)
@@ -306,8 +317,14 @@ __global__ void __launch_bounds__(RL_NT) attn_bwd_kernel(const rl_attn_bwd_args 
     for (int i = tid; i < LC; i += RL_NT) {
       const int t = i / C, c = i % C;
       dxw[i] = su[t * LDC + c] + (resid ? __ldg(gw + i) : 0.f);
-      uw[i] = __ldg(xw + i);
+      if (FW) su[t * LDC + c] = __ldg(xw + i); else uw[i] = __ldg(xw + i);
     }
+    __syncthreads();
+  }
+  if (FW) {   // dWq = dq^T u, dWkv = [dk | dv]^T u  (u now sits in su)
+    cta_wgrad<C, C, L>(sdq, LDC, su, LDC, a.d_wq, a.d_bq);
+    cta_wgrad<C, C, L>(sdk, LDC, su, LDC, a.d_wkv, a.d_bkv);
+    cta_wgrad<C, C, L>(sdv, LDC, su, LDC, a.d_wkv ? a.d_wkv + C * C : nullptr, a.d_bkv ? a.d_bkv + C : nullptr);
   }
   if (a.d_table && W > 0)
     for (int i = tid; i < (2 * W - 1) * H; i += RL_NT) atomicAdd(a.d_table + i, stabg[i]);
@@ -319,10 +336,10 @@ int launch_fwd(const rl_attn_fwd_args* a, cudaStream_t st) {
   const size_t smem = attn_fwd_smem<C>(a->L);
   if (win == 1) {
     if (int rc = rl_set_smem(attn_fwd_kernel<C, 1>, smem)) return rc;
-    attn_fwd_kernel<C, 1><<<a->B, RL_NT, smem, st>>>(*a);
+    rl_launch_pdl(attn_fwd_kernel<C, 1>, dim3(a->B), dim3(RL_NT), smem, st, *a);
   } else {
     if (int rc = rl_set_smem(attn_fwd_kernel<C, 2>, smem)) return rc;
-    attn_fwd_kernel<C, 2><<<a->B, RL_NT, smem, st>>>(*a);
+    rl_launch_pdl(attn_fwd_kernel<C, 2>, dim3(a->B), dim3(RL_NT), smem, st, *a);
   }
   return rl_check_launch("attn_fwd_kernel", C);
 }
@@ -333,10 +350,10 @@ int launch_bwd(const rl_attn_bwd_args* a, cudaStream_t st) {
   const size_t smem = attn_bwd_smem<C>(a->L);
   if (win == 1) {
     if (int rc = rl_set_smem(attn_bwd_kernel<C, 1>, smem)) return rc;
-    attn_bwd_kernel<C, 1><<<a->B, RL_NT, smem, st>>>(*a);
+    rl_launch_pdl(attn_bwd_kernel<C, 1>, dim3(a->B), dim3(RL_NT), smem, st, *a);
   } else {
     if (int rc = rl_set_smem(attn_bwd_kernel<C, 2>, smem)) return rc;
-    attn_bwd_kernel<C, 2><<<a->B, RL_NT, smem, st>>>(*a);
+    rl_launch_pdl(attn_bwd_kernel<C, 2>, dim3(a->B), dim3(RL_NT), smem, st, *a);
   }
   return rl_check_launch("attn_bwd_kernel", C);
 }
@@ -391,6 +408,7 @@ extern "C" int ralenet_attn_bwd(const rl_attn_bwd_args* a, void* stream) {
   }
   if (rc) return rc;
   const int M = a->B * a->L, C = a->C;
+  if (C <= 16) return RL_OK;        // narrow stages accumulate their weight gradients inside the kernel
   const RlWgradDesc d[3] = {{a->g, C, a->o, C, C, C, a->d_wp, a->d_bp},
                             {a->dqkv, 3 * C, a->u, C, C, C, a->d_wq, a->d_bq},
                             {a->dqkv + C, 3 * C, a->u, C, 2 * C, C, a->d_wkv, a->d_bkv}};

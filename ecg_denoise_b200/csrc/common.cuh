@@ -5,7 +5,12 @@
 #include <stdio.h>
 #include "ralenet_b200.h"
 
-#define RL_NT 256          // threads per CTA for all window kernels
+#ifndef RL_NT
+#define RL_NT 256          // threads per CTA (a translation unit may define it before including this header)
+#endif
+#ifndef RL_MINB
+#define RL_MINB 1          // min CTAs per SM hint for __launch_bounds__
+#endif
 #define RL_HD 4            // head dim (model/transformer.py:277: dim // num_heads == 4 at every stage)
 #define RL_LOG2E 1.4426950408889634f
 #define RL_LN_EPS 1e-5f
@@ -21,6 +26,26 @@ int rl_check_launch(const char* what, int tag0 = -1, int tag1 = -1);
       return (code);                           \
     }                                          \
   } while (0)
+
+// Programmatic dependent launch: the kernel may be scheduled while the previous kernel on the stream drains;
+// it must call pdl_wait() before touching global memory.  Captured into CUDA graphs as programmatic edges.
+template <typename... KArgs, typename... Args>
+static inline void rl_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);      // errors surface through rl_check_launch()
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 template <typename K>
 static inline int rl_set_smem(K kernel, size_t bytes) {
@@ -497,6 +522,49 @@ struct WStream {
     }
   }
 };
+
+// ---------------------------------------------------------------------------------------------
+// In-CTA weight gradient for the narrow stages (C <= 16), where a separate GEMM launch costs more than the math:
+//   dW[n*K + k] += sum_{t<L} A[t*lda + n] * B[t*ldb + k]      db[n] += sum_t A[t*lda + n]
+// one partial per CTA (window), finished with fp32 red.global.  All RL_NT threads must call.
+template <int N, int K, int L>
+__device__ __forceinline__ void cta_wgrad(const float* A, int lda, const float* B, int ldb, float* __restrict__ dW,
+                                          float* __restrict__ db) {
+  constexpr int OUT = N * K;
+  const int tid = threadIdx.x;
+  if (dW != nullptr) {
+    if (OUT >= RL_NT) {
+      static_assert(OUT < RL_NT || OUT % RL_NT == 0, "cta_wgrad: outputs must tile the CTA");
+      constexpr int R = (OUT >= RL_NT) ? OUT / RL_NT : 1;
+      float acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll 4
+      for (int t = 0; t < L; ++t) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int o = tid + r * RL_NT;
+          acc[r] = fmaf(A[t * lda + o / K], B[t * ldb + o % K], acc[r]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) atomicAdd(dW + tid + r * RL_NT, acc[r]);
+    } else {
+      constexpr int G = (OUT < RL_NT) ? RL_NT / OUT : 1;          // token groups
+      const int o = tid % OUT, grp = tid / OUT;
+      float acc = 0.f;
+      if (grp < G)
+        for (int t = grp; t < L; t += G) acc = fmaf(A[t * lda + o / K], B[t * ldb + o % K], acc);
+      if (grp < G) atomicAdd(dW + o, acc);
+    }
+  }
+  if (db != nullptr && tid < N) {
+    float s = 0.f;
+#pragma unroll 4
+    for (int t = 0; t < L; ++t) s += A[t * lda + tid];
+    atomicAdd(db + tid, s);
+  }
+}
 
 // generic weight-gradient GEMM launcher (wgrad.cu):
 //   dW[n*K + k] += sum_m dY[m*ldy + n] * X[m*ldx + k]      n < N, k < K, m < M

@@ -7,6 +7,8 @@
 // 3-tap FIR along the tokens on hidden channel 0 only, followed by a second GELU on all channels
 // (SURVEY.md F5); RL_LE_DEPTHWISE applies per-channel FIRs to all 4C channels; RL_LE_NONE is the plain MLP.
 // The L x 4C hidden activation (8192 floats per window) stays in shared memory between the two GEMMs.
+#define RL_NT 512        // 16 warps per window: the benchmark batch (256 windows on 148 SMs) needs the parallelism
+#define RL_MINB 2
 #include "common.cuh"
 
 namespace {
@@ -21,7 +23,9 @@ size_t ffn_fwd_smem(int L) {
 }
 
 template <int C, int WIN>
-__global__ void __launch_bounds__(RL_NT) ffn_fwd_kernel(const rl_ffn_fwd_args a) {
+__global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_kernel(const rl_ffn_fwd_args a) {
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   extern __shared__ __align__(16) float smem[];
   constexpr int L = 2048 * WIN / C;
   constexpr int LDC = ld_mk(C);
@@ -118,12 +122,15 @@ __host__ __device__ constexpr int ffn_bwd_swf() {
 }
 template <int C>
 size_t ffn_bwd_smem(int L, bool dw) {
-  return sizeof(float) * (2 * (size_t)L * ld_mk(C) + (dw ? 2 : 1) * (size_t)L * ld_mk(4 * C) + ffn_bwd_swf<C>() +
-                          3 * (size_t)L + 2 * C + 64);
+  // narrow stages (C <= 16) keep g2 in shared memory as well for the in-CTA weight gradients
+  return sizeof(float) * (2 * (size_t)L * ld_mk(C) + ((dw ? 2 : 1) + (C <= 16 ? 1 : 0)) * (size_t)L * ld_mk(4 * C) +
+                          ffn_bwd_swf<C>() + 3 * (size_t)L + 2 * C + 64);
 }
 
 template <int C, int WIN, bool DW>
-__global__ void __launch_bounds__(RL_NT) ffn_bwd_kernel(const rl_ffn_bwd_args a) {
+__global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bwd_args a) {
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   extern __shared__ __align__(16) float smem[];
   constexpr int L = 2048 * WIN / C;
   constexpr int LDC = ld_mk(C);
@@ -132,7 +139,9 @@ __global__ void __launch_bounds__(RL_NT) ffn_bwd_kernel(const rl_ffn_bwd_args a)
   float* su = sg + L * LDC;               // du (LN2 output gradient)
   float* sd = su + L * LDC;               // df / dh
   float* sh = sd + L * LDH;               // g1 = GELU(h), depthwise mode only
-  float* sw = sh + (DW ? L * LDH : 0);
+  constexpr bool FW = (C <= 16);          // narrow stages: weight gradients accumulated in-CTA (no wgrad launch)
+  float* sg2 = sh + (DW ? L * LDH : 0);   // g2, narrow stages only
+  float* sw = sg2 + (FW ? L * LDH : 0);
   float* sg10 = sw + ffn_bwd_swf<C>();    // g1[:,0]
   float* sf0 = sg10 + L;                  // fir(g1[:,0])
   float* sdf0 = sf0 + L;                  // df[:,0]
@@ -170,8 +179,9 @@ __global__ void __launch_bounds__(RL_NT) ffn_bwd_kernel(const rl_ffn_bwd_args a)
       const int t = i / HC, n = i % HC;
       const float p = (t > 0) ? sh[(t - 1) * LDH + n] : 0.f;
       const float nx = (t + 1 < L) ? sh[(t + 1) * LDH + n] : 0.f;
-      g2w[i] = gelu_f(__ldg(a.lew + 3 * n) * p + __ldg(a.lew + 3 * n + 1) * sh[t * LDH + n] +
-                      __ldg(a.lew + 3 * n + 2) * nx);
+      const float g2v = gelu_f(__ldg(a.lew + 3 * n) * p + __ldg(a.lew + 3 * n + 1) * sh[t * LDH + n] +
+                               __ldg(a.lew + 3 * n + 2) * nx);
+      if (FW) sg2[t * LDH + n] = g2v; else g2w[i] = g2v;
     }
   }
 
@@ -191,22 +201,22 @@ __global__ void __launch_bounds__(RL_NT) ffn_bwd_kernel(const rl_ffn_bwd_args a)
         float g1, d1;
         gelu_both(__ldg(hw + t * HC + n), g1, d1);
         if (mode == RL_LE_NONE) {
-          g2w[t * HC + n] = g1;
+          if (FW) sg2[t * LDH + n] = g1; else g2w[t * HC + n] = g1;
           const float dh = v * d1;
           sd[t * LDH + n] = dh;
-          dhw[t * HC + n] = dh;
+          if (!FW) dhw[t * HC + n] = dh;
         } else if (n == 0) {                           // partial, convolved channel: finish after the FIR adjoint
           float g2, d2;
           gelu_both(sf0[t], g2, d2);
-          g2w[t * HC] = g2;
+          if (FW) sg2[t * LDH] = g2; else g2w[t * HC] = g2;
           sdf0[t] = v * d2;
         } else {                                       // partial, untouched channel: f == g1
           float g2, d2;
           gelu_both(g1, g2, d2);
-          g2w[t * HC + n] = g2;
+          if (FW) sg2[t * LDH + n] = g2; else g2w[t * HC + n] = g2;
           const float dh = v * d2 * d1;
           sd[t * LDH + n] = dh;
-          dhw[t * HC + n] = dh;
+          if (!FW) dhw[t * HC + n] = dh;
         }
       }
     });
@@ -220,7 +230,7 @@ __global__ void __launch_bounds__(RL_NT) ffn_bwd_kernel(const rl_ffn_bwd_args a)
         const float dg1 = lw0 * dn + lw1 * d + lw2 * dp;            // adjoint of the 3-tap FIR
         const float dh = dg1 * gelu_grad_f(__ldg(hw + t * HC));
         sd[t * LDH] = dh;
-        dhw[t * HC] = dh;
+        if (!FW) dhw[t * HC] = dh;
         a0 += d * ((t > 0) ? sg10[t - 1] : 0.f);
         a1 += d * sg10[t];
         a2 += d * ((t + 1 < L) ? sg10[t + 1] : 0.f);
@@ -249,7 +259,7 @@ __global__ void __launch_bounds__(RL_NT) ffn_bwd_kernel(const rl_ffn_bwd_args a)
           a2 += dcur * ((t + 1 < L) ? sh[(t + 1) * LDH + c] : 0.f);
           const float dh = dg1 * gelu_grad_f(__ldg(hw + t * HC + c));
           sd[t * LDH + c] = dh;
-          dhw[t * HC + c] = dh;
+          if (!FW) dhw[t * HC + c] = dh;
           dprev = dcur;
           dcur = dnxt;
         }
@@ -283,7 +293,8 @@ __global__ void __launch_bounds__(RL_NT) ffn_bwd_kernel(const rl_ffn_bwd_args a)
         L, lw, s_gb, [&](int t, int c) { return __ldg(xw + t * C + c); }, [&](int t, int c) { return su[t * LDC + c]; },
         [&](int t, int c, float dz, float zh) {
           dxw[t * C + c] = (resid ? sg[t * LDC + c] : 0.f) + dz;
-          uw[t * C + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c));
+          const float u = fmaf(zh, __ldg(lw + c), __ldg(lb + c));
+          if (FW) su[t * LDC + c] = u; else uw[t * C + c] = u;      // du at (t, c) was consumed by this thread
         });
     __syncthreads();
     if (a.d_ln_w)
@@ -295,8 +306,13 @@ __global__ void __launch_bounds__(RL_NT) ffn_bwd_kernel(const rl_ffn_bwd_args a)
     for (int i = tid; i < L * C; i += RL_NT) {
       const int t = i / C, c = i % C;
       dxw[i] = su[t * LDC + c] + (resid ? sg[t * LDC + c] : 0.f);
-      uw[i] = __ldg(xw + i);
+      if (FW) su[t * LDC + c] = __ldg(xw + i); else uw[i] = __ldg(xw + i);
     }
+    __syncthreads();
+  }
+  if (FW) {   // dW2 = g^T g2, dW1 = dh^T u   (u now sits in su)
+    cta_wgrad<C, HC, L>(sg, LDC, sg2, LDH, a.d_w2, a.d_b2);
+    cta_wgrad<HC, C, L>(sd, LDH, su, LDC, a.d_w1, a.d_b1);
   }
 }
 
@@ -305,10 +321,10 @@ int launch_fwd(const rl_ffn_fwd_args* a, cudaStream_t st) {
   const size_t smem = ffn_fwd_smem<C>(a->L);
   if (a->L * C == 2048) {
     if (int rc = rl_set_smem(ffn_fwd_kernel<C, 1>, smem)) return rc;
-    ffn_fwd_kernel<C, 1><<<a->B, RL_NT, smem, st>>>(*a);
+    rl_launch_pdl(ffn_fwd_kernel<C, 1>, dim3(a->B), dim3(RL_NT), smem, st, *a);
   } else {
     if (int rc = rl_set_smem(ffn_fwd_kernel<C, 2>, smem)) return rc;
-    ffn_fwd_kernel<C, 2><<<a->B, RL_NT, smem, st>>>(*a);
+    rl_launch_pdl(ffn_fwd_kernel<C, 2>, dim3(a->B), dim3(RL_NT), smem, st, *a);
   }
   return rl_check_launch("ffn_fwd_kernel", C);
 }
@@ -317,7 +333,7 @@ template <int C, int WIN, bool DW>
 int launch_bwd_one(const rl_ffn_bwd_args* a, cudaStream_t st) {
   const size_t smem = ffn_bwd_smem<C>(a->L, DW);
   if (int rc = rl_set_smem(ffn_bwd_kernel<C, WIN, DW>, smem)) return rc;
-  ffn_bwd_kernel<C, WIN, DW><<<a->B, RL_NT, smem, st>>>(*a);
+  rl_launch_pdl(ffn_bwd_kernel<C, WIN, DW>, dim3(a->B), dim3(RL_NT), smem, st, *a);
   return rl_check_launch("ffn_bwd_kernel", C);
 }
 
@@ -374,6 +390,7 @@ extern "C" int ralenet_ffn_bwd(const rl_ffn_bwd_args* a, void* stream) {
   }
   if (rc) return rc;
   const int M = a->B * a->L, C = a->C;
+  if (C <= 16) return RL_OK;        // narrow stages accumulate their weight gradients inside the kernel
   const RlWgradDesc d[2] = {{a->g, C, a->g2, 4 * C, C, 4 * C, a->d_w2, a->d_b2},
                             {a->dh, 4 * C, a->u, C, 4 * C, C, a->d_w1, a->d_b1}};
   return rl_launch_wgrad_group(d, 2, M, st);

@@ -5,6 +5,8 @@
 //   separate (model/transformer.py:418-424): 'b l (c1 c2) -> b (c1 l) c2' -> LN(C/2) -> Linear(C/2,C/2,no bias)
 //            rows 0..L-1 take channels [0,C/2), rows L..2L-1 take [C/2,C); + U-skip (:650,654,658).
 // Both are "rows x Cn" LayerNorm + square GEMM with rows*Cn = L*C; templated on Cn.
+#define RL_NT 512        // 16 warps per window: the benchmark batch (256 windows on 148 SMs) needs the parallelism
+#define RL_MINB 2
 #include "common.cuh"
 
 namespace {
@@ -23,7 +25,9 @@ template <int CN>
 size_t patch_smem(int rows) { return sizeof(float) * (2 * (size_t)rows * ld_mk(CN) + patch_swf<CN>() + 2 * CN + 64); }
 
 template <int CN, int WIN>
-__global__ void __launch_bounds__(RL_NT) patch_fwd_kernel(const rl_patch_fwd_args a) {
+__global__ void __launch_bounds__(RL_NT, RL_MINB) patch_fwd_kernel(const rl_patch_fwd_args a) {
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   extern __shared__ __align__(16) float smem[];
   constexpr int LDA = ld_mk(CN);
   constexpr int rows = 2048 * WIN / CN;
@@ -57,7 +61,9 @@ __global__ void __launch_bounds__(RL_NT) patch_fwd_kernel(const rl_patch_fwd_arg
 }
 
 template <int CN, int WIN>
-__global__ void __launch_bounds__(RL_NT) patch_bwd_kernel(const rl_patch_bwd_args a, float* __restrict__ gsum) {
+__global__ void __launch_bounds__(RL_NT, RL_MINB) patch_bwd_kernel(const rl_patch_bwd_args a, float* __restrict__ gsum) {
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   extern __shared__ __align__(16) float smem[];
   constexpr int LDA = ld_mk(CN);
   constexpr int rows = 2048 * WIN / CN;
@@ -107,10 +113,10 @@ int launch_fwd(const rl_patch_fwd_args* a, cudaStream_t st) {
   const size_t smem = patch_smem<CN>(rows);
   if (a->L * a->C == 2048) {
     if (int rc = rl_set_smem(patch_fwd_kernel<CN, 1>, smem)) return rc;
-    patch_fwd_kernel<CN, 1><<<a->B, RL_NT, smem, st>>>(*a);
+    rl_launch_pdl(patch_fwd_kernel<CN, 1>, dim3(a->B), dim3(RL_NT), smem, st, *a);
   } else {
     if (int rc = rl_set_smem(patch_fwd_kernel<CN, 2>, smem)) return rc;
-    patch_fwd_kernel<CN, 2><<<a->B, RL_NT, smem, st>>>(*a);
+    rl_launch_pdl(patch_fwd_kernel<CN, 2>, dim3(a->B), dim3(RL_NT), smem, st, *a);
   }
   return rl_check_launch("patch_fwd_kernel", CN);
 }
@@ -121,10 +127,10 @@ int launch_bwd(const rl_patch_bwd_args* a, float* gsum, cudaStream_t st) {
   const size_t smem = patch_smem<CN>(rows);
   if (a->L * a->C == 2048) {
     if (int rc = rl_set_smem(patch_bwd_kernel<CN, 1>, smem)) return rc;
-    patch_bwd_kernel<CN, 1><<<a->B, RL_NT, smem, st>>>(*a, gsum);
+    rl_launch_pdl(patch_bwd_kernel<CN, 1>, dim3(a->B), dim3(RL_NT), smem, st, *a, gsum);
   } else {
     if (int rc = rl_set_smem(patch_bwd_kernel<CN, 2>, smem)) return rc;
-    patch_bwd_kernel<CN, 2><<<a->B, RL_NT, smem, st>>>(*a, gsum);
+    rl_launch_pdl(patch_bwd_kernel<CN, 2>, dim3(a->B), dim3(RL_NT), smem, st, *a, gsum);
   }
   return rl_check_launch("patch_bwd_kernel", CN);
 }

@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(RL_NT) reduce16_kernel(const float* __restrict
 }
 
 __global__ void __launch_bounds__(RL_NT) stem_apply_kernel(const rl_stem_args a) {
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   __shared__ float sx[2 * (MAXL + 2)];
   __shared__ float sw[48], sb[8], smu[8], srs[8], sgam[8], sbet[8];
   const int L = a.L, tid = threadIdx.x;
@@ -138,6 +140,8 @@ __device__ __forceinline__ void stem_mu_rstd(const rl_stem_bwd_args& a, int o, f
 
 // per-window sums of g and g*ahat per channel -> partials[b][16]  ([0:8] = sum g, [8:16] = sum g*ahat)
 __global__ void __launch_bounds__(RL_NT) stem_bwd_stats_kernel(const rl_stem_bwd_args a) {
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   __shared__ float sx[2 * (MAXL + 2)];
   __shared__ float sw[48], sb[8], smu[8], srs[8];
   __shared__ float sacc[16];
@@ -182,6 +186,8 @@ __global__ void __launch_bounds__(RL_NT) stem_bwd_stats_kernel(const rl_stem_bwd
 }
 
 __global__ void __launch_bounds__(RL_NT) stem_bwd_apply_kernel(const rl_stem_bwd_args a) {
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   __shared__ float sx[2 * (MAXL + 2)];
   __shared__ float sdc[8 * (MAXL + 2)];
   __shared__ float sw[48], sb[8], smu[8], srs[8], sgam[8], sm1[8], sm2[8];
@@ -267,6 +273,8 @@ __global__ void __launch_bounds__(RL_NT) stem_bwd_apply_kernel(const rl_stem_bwd
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RL_NT) head_fwd_kernel(const rl_head_fwd_args a) {
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   __shared__ float ss[(MAXL + 2) * 8];
   __shared__ float sw[48], sb[2];
   const int L = a.L, tid = threadIdx.x;
@@ -297,6 +305,8 @@ __global__ void __launch_bounds__(RL_NT) head_fwd_kernel(const rl_head_fwd_args 
 }
 
 __global__ void __launch_bounds__(RL_NT) head_bwd_kernel(const rl_head_bwd_args a) {
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   __shared__ float ss[(MAXL + 2) * 8];
   __shared__ float sdo[2 * (MAXL + 2)];
   __shared__ float sw[48];
@@ -369,6 +379,8 @@ __global__ void __launch_bounds__(RL_NT) head_bwd_kernel(const rl_head_bwd_args 
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RL_NT) mse_kernel(const rl_mse_args a) {
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   __shared__ float s_red[32];
   const int per = a.per, tid = threadIdx.x;
   const size_t off = (size_t)blockIdx.x * per;
@@ -548,7 +560,7 @@ extern "C" int ralenet_stem_apply(const rl_stem_args* a, void* stream) {
   RL_REQUIRE(a->x && a->conv_w && a->conv_b && a->bn_w && a->bn_b && a->y && a->running_mean && a->running_var,
              RL_ERR_NULL, "stem_apply: NULL tensor");
   RL_REQUIRE(!a->training || a->stats, RL_ERR_NULL, "stem_apply: training needs stats");
-  stem_apply_kernel<<<a->B, RL_NT, 0, (cudaStream_t)stream>>>(*a);
+  rl_launch_pdl(stem_apply_kernel, dim3(a->B), dim3(RL_NT), 0, (cudaStream_t)stream, *a);
   return rl_check_launch("stem_apply_kernel");
 }
 
@@ -560,7 +572,7 @@ extern "C" int ralenet_stem_bwd_stats(const rl_stem_bwd_args* a, void* stream) {
   RL_REQUIRE(a->training ? (a->stats != nullptr) : (a->running_var && a->running_mean), RL_ERR_NULL,
              "stem_bwd_stats: needs stats (training) or running stats (eval)");
   cudaStream_t st = (cudaStream_t)stream;
-  stem_bwd_stats_kernel<<<a->B, RL_NT, 0, st>>>(*a);
+  rl_launch_pdl(stem_bwd_stats_kernel, dim3(a->B), dim3(RL_NT), 0, st, *a);
   if (int rc = rl_check_launch("stem_bwd_stats_kernel")) return rc;
   reduce16_kernel<<<1, RL_NT, 0, st>>>(a->partials, a->B, a->sums, -1.f, a->d_bn_w, a->d_bn_b);
   return rl_check_launch("reduce16_kernel");
@@ -573,7 +585,7 @@ extern "C" int ralenet_stem_bwd_apply(const rl_stem_bwd_args* a, void* stream) {
   RL_REQUIRE(a->training ? (a->stats != nullptr) : (a->running_var && a->running_mean), RL_ERR_NULL,
              "stem_bwd_apply: needs stats (training) or running stats (eval)");
   RL_REQUIRE(!a->d_conv_w == !a->d_conv_b, RL_ERR_NULL, "stem_bwd_apply: d_conv_w/d_conv_b both or neither");
-  stem_bwd_apply_kernel<<<a->B, RL_NT, 0, (cudaStream_t)stream>>>(*a);
+  rl_launch_pdl(stem_bwd_apply_kernel, dim3(a->B), dim3(RL_NT), 0, (cudaStream_t)stream, *a);
   return rl_check_launch("stem_bwd_apply_kernel");
 }
 
@@ -581,7 +593,7 @@ extern "C" int ralenet_head_fwd(const rl_head_fwd_args* a, void* stream) {
   RL_REQUIRE(a, RL_ERR_NULL, "head_fwd: args is NULL");
   if (int rc = check_BL("head_fwd", a->B, a->L)) return rc;
   RL_REQUIRE(a->x && a->w && a->b && a->out, RL_ERR_NULL, "head_fwd: NULL tensor");
-  head_fwd_kernel<<<a->B, RL_NT, 0, (cudaStream_t)stream>>>(*a);
+  rl_launch_pdl(head_fwd_kernel, dim3(a->B), dim3(RL_NT), 0, (cudaStream_t)stream, *a);
   return rl_check_launch("head_fwd_kernel");
 }
 
@@ -590,7 +602,7 @@ extern "C" int ralenet_head_bwd(const rl_head_bwd_args* a, void* stream) {
   if (int rc = check_BL("head_bwd", a->B, a->L)) return rc;
   RL_REQUIRE(a->dout && a->x && a->w && a->ds, RL_ERR_NULL, "head_bwd: NULL tensor");
   RL_REQUIRE(!a->d_w == !a->d_b, RL_ERR_NULL, "head_bwd: d_w/d_b both or neither");
-  head_bwd_kernel<<<a->B, RL_NT, 0, (cudaStream_t)stream>>>(*a);
+  rl_launch_pdl(head_bwd_kernel, dim3(a->B), dim3(RL_NT), 0, (cudaStream_t)stream, *a);
   return rl_check_launch("head_bwd_kernel");
 }
 
@@ -598,7 +610,7 @@ extern "C" int ralenet_mse(const rl_mse_args* a, void* stream) {
   RL_REQUIRE(a, RL_ERR_NULL, "mse: args is NULL");
   RL_REQUIRE(a->B > 0 && a->per > 0, RL_ERR_SHAPE, "mse: B=%d per=%d", a->B, a->per);
   RL_REQUIRE(a->pred && a->target && a->loss, RL_ERR_NULL, "mse: NULL tensor");
-  mse_kernel<<<a->B, RL_NT, 0, (cudaStream_t)stream>>>(*a);
+  rl_launch_pdl(mse_kernel, dim3(a->B), dim3(RL_NT), 0, (cudaStream_t)stream, *a);
   return rl_check_launch("mse_kernel");
 }
 

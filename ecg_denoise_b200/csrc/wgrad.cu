@@ -13,6 +13,8 @@ template <int TN, int TK>
 __global__ void __launch_bounds__(RL_NT) wgrad_kernel(const float* __restrict__ dY, int ldy,
                                                       const float* __restrict__ X, int ldx, int M, int N, int K,
                                                       float* __restrict__ dW, float* __restrict__ db, int MC) {
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   constexpr int RM = (TN >= 16) ? TN / 16 : 1;
   constexpr int RN = (TK >= 16) ? TK / 16 : 1;
   constexpr int NTN = TK / RN;                 // threads along k
@@ -79,7 +81,7 @@ int launch(const float* dY, int ldy, const float* X, int ldx, int M, int N, int 
   MC = ((MC + MS - 1) / MS) * MS;
   splits = (M + MC - 1) / MC;
   dim3 grid(tiles, splits);
-  wgrad_kernel<TN, TK><<<grid, RL_NT, 0, st>>>(dY, ldy, X, ldx, M, N, K, dW, db, MC);
+  rl_launch_pdl(wgrad_kernel<TN, TK>, dim3(grid), dim3(RL_NT), 0, st, dY, ldy, X, ldx, M, N, K, dW, db, MC);
   return rl_check_launch("wgrad_kernel", N, K);
 }
 
@@ -125,6 +127,8 @@ constexpr int WG_MS = 64;   // tokens per pipeline stage
 
 template <int T>
 __global__ void __launch_bounds__(RL_NT) wgrad_group_kernel(const WgGroup grp) {
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   constexpr int LD = T + 8;                     // % 32 in {8, 24}: conflict-free A_KM / B_KN fragment loads
   extern __shared__ __align__(16) float smem[];
   float* sA = smem;                             // [2][WG_MS][LD]  dY tile
@@ -200,7 +204,7 @@ int launch_group(WgGroup& g, int total_tiles, cudaStream_t st) {
   const size_t smem = sizeof(float) * 4 * WG_MS * (T + 8);
   if (int rc = rl_set_smem(wgrad_group_kernel<T>, smem)) return rc;
   dim3 grid(total_tiles, splits);
-  wgrad_group_kernel<T><<<grid, RL_NT, smem, st>>>(g);
+  rl_launch_pdl(wgrad_group_kernel<T>, dim3(grid), dim3(RL_NT), smem, st, g);
   return rl_check_launch("wgrad_group_kernel", T, total_tiles);
 }
 

@@ -11,6 +11,10 @@
 #define RL_MINB 2
 #include "common.cuh"
 
+// cluster kernels for the wide stages (ffn_cluster.cu); return 1 when the shape/mode is not handled there
+int rl_ffn_fwd_cluster(const rl_ffn_fwd_args* a, cudaStream_t st);
+int rl_ffn_bwd_cluster(const rl_ffn_bwd_args* a, cudaStream_t st);
+
 namespace {
 
 template <int C>
@@ -361,6 +365,10 @@ extern "C" int ralenet_ffn_fwd(const rl_ffn_fwd_args* a, void* stream) {
   RL_REQUIRE(!(a->flags & RL_F_PRENORM) || (a->ln_w && a->ln_b), RL_ERR_NULL, "ffn_fwd: prenorm needs ln");
   RL_REQUIRE(a->le_mode == RL_LE_NONE || a->lew, RL_ERR_NULL, "ffn_fwd: le_mode needs lew");
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int rc = rl_ffn_fwd_cluster(a, st);
+    if (rc <= 0) return rc;
+  }
   switch (a->C) {
     case 8: return launch_fwd<8>(a, st);
     case 16: return launch_fwd<16>(a, st);
@@ -380,8 +388,9 @@ extern "C" int ralenet_ffn_bwd(const rl_ffn_bwd_args* a, void* stream) {
   RL_REQUIRE(a->le_mode == RL_LE_NONE || a->lew, RL_ERR_NULL, "ffn_bwd: le_mode needs lew");
   RL_REQUIRE(!a->d_ln_w == !a->d_ln_b, RL_ERR_NULL, "ffn_bwd: d_ln_w/d_ln_b must be both set or both NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = RL_ERR_SHAPE;
-  switch (a->C) {
+  int rc = rl_ffn_bwd_cluster(a, st);
+  if (rc < 0) return rc;
+  if (rc == 1) switch (a->C) {
     case 8: rc = launch_bwd<8>(a, st); break;
     case 16: rc = launch_bwd<16>(a, st); break;
     case 32: rc = launch_bwd<32>(a, st); break;

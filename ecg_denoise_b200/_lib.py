@@ -67,7 +67,7 @@ def _parse_header(path: str):
                     ctype = ctype * (consts[d] if d in consts else int(d))
                 fields.append((fname, ctype))
         structs[name] = type(name, (ctypes.Structure,), {"_fields_": fields})
-    funcs = re.findall(r"^\s*(?:int|uint64_t|int64_t|const char\*)\s+(ralenet_\w+)\s*\(", src, flags=re.M)
+    funcs = re.findall(r"^\s*(?:int|int32_t|uint64_t|int64_t|const char\*)\s+(ralenet_\w+)\s*\(", src, flags=re.M)
     return consts, structs, sorted(set(funcs))
 
 

@@ -25,11 +25,20 @@ struct Prof {
   cudaStream_t stream = nullptr;
   int n = 0;
   cudaEvent_t ev[kMaxProf + 1];
+  cudaEvent_t pre[kMaxProf];       // optional event right before a launch (excludes host-side gaps)
+  bool has_pre[kMaxProf];
   int created = 0;
   char label[kMaxProf][48];
 };
 Prof g_prof;
 }  // namespace
+
+void rl_prof_pre(cudaStream_t st) {
+  if (g_prof.on && g_prof.n < kMaxProf && st == g_prof.stream) {
+    cudaEventRecord(g_prof.pre[g_prof.n], st);
+    g_prof.has_pre[g_prof.n] = true;
+  }
+}
 
 int rl_check_launch(const char* what, int t0, int t1) {
   cudaError_t e = cudaGetLastError();
@@ -50,6 +59,10 @@ int rl_check_launch(const char* what, int t0, int t1) {
 
 extern "C" int ralenet_profile_begin(void* stream) {
   while (g_prof.created <= kMaxProf) {
+    if (g_prof.created < kMaxProf && cudaEventCreate(&g_prof.pre[g_prof.created]) != cudaSuccess) {
+      rl_set_error("profile_begin: cudaEventCreate failed");
+      return RL_ERR_CUDA;
+    }
     if (cudaEventCreate(&g_prof.ev[g_prof.created]) != cudaSuccess) {
       rl_set_error("profile_begin: cudaEventCreate failed");
       return RL_ERR_CUDA;
@@ -58,6 +71,7 @@ extern "C" int ralenet_profile_begin(void* stream) {
   }
   g_prof.stream = (cudaStream_t)stream;
   g_prof.n = 0;
+  for (int i = 0; i < kMaxProf; ++i) g_prof.has_pre[i] = false;
   g_prof.on = true;
   cudaEventRecord(g_prof.ev[0], g_prof.stream);
   return RL_OK;
@@ -71,7 +85,7 @@ extern "C" int ralenet_profile_end(char* labels, int32_t label_stride, float* ms
     return RL_ERR_CUDA;
   }
   for (int i = 0; i < n; ++i) {
-    cudaEventElapsedTime(&ms[i], g_prof.ev[i], g_prof.ev[i + 1]);
+    cudaEventElapsedTime(&ms[i], g_prof.has_pre[i] ? g_prof.pre[i] : g_prof.ev[i], g_prof.ev[i + 1]);
     snprintf(labels + (size_t)i * label_stride, label_stride, "%s", g_prof.label[i]);
   }
   return n;

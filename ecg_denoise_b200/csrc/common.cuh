@@ -18,6 +18,7 @@
 void rl_set_error(const char* fmt, ...);
 void rl_count_launch();
 int rl_check_launch(const char* what, int tag0 = -1, int tag1 = -1);
+void rl_prof_pre(cudaStream_t st);     // profiling: event right before the next launch on the profiled stream
 
 #define RL_REQUIRE(cond, code, ...)            \
   do {                                         \
@@ -42,6 +43,7 @@ static inline void rl_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  rl_prof_pre(st);
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);      // errors surface through rl_check_launch()
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

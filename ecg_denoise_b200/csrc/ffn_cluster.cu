@@ -355,6 +355,7 @@ int launch_cluster(void (*kernel)(const Args), size_t smem, int B, const Args& a
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
+  rl_prof_pre(st);
   cudaLaunchKernelEx(&cfg, kernel, a);
   return rl_check_launch(name, C);
 }

@@ -548,8 +548,10 @@ extern "C" int ralenet_stem_stats(const rl_stem_args* a, void* stream) {
   if (int rc = check_BL("stem_stats", a->B, a->L)) return rc;
   RL_REQUIRE(a->x && a->conv_w && a->conv_b && a->stats && a->partials, RL_ERR_NULL, "stem_stats: NULL tensor");
   cudaStream_t st = (cudaStream_t)stream;
+  rl_prof_pre(st);
   stem_stats_kernel<<<a->B, RL_NT, 0, st>>>(*a);
   if (int rc = rl_check_launch("stem_stats_kernel")) return rc;
+  rl_prof_pre(st);
   reduce16_kernel<<<1, RL_NT, 0, st>>>(a->partials, a->B, a->stats, (float)a->B * (float)a->L, nullptr, nullptr);
   return rl_check_launch("reduce16_kernel");
 }
@@ -574,6 +576,7 @@ extern "C" int ralenet_stem_bwd_stats(const rl_stem_bwd_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   rl_launch_pdl(stem_bwd_stats_kernel, dim3(a->B), dim3(RL_NT), 0, st, *a);
   if (int rc = rl_check_launch("stem_bwd_stats_kernel")) return rc;
+  rl_prof_pre(st);
   reduce16_kernel<<<1, RL_NT, 0, st>>>(a->partials, a->B, a->sums, -1.f, a->d_bn_w, a->d_bn_b);
   return rl_check_launch("reduce16_kernel");
 }
@@ -630,6 +633,7 @@ extern "C" int ralenet_conv1d_fwd(const rl_conv_fwd_args* a, void* stream) {
   if (int rc = conv_check(a->B, a->L, a->Cin, a->Cout, a->K, &smem, false)) return rc;
   RL_REQUIRE(a->x && a->w && a->y, RL_ERR_NULL, "conv1d_fwd: NULL tensor");
   if (int rc = rl_set_smem(conv1d_fwd_kernel, smem)) return rc;
+  rl_prof_pre((cudaStream_t)stream);
   conv1d_fwd_kernel<<<a->B, RL_NT, smem, (cudaStream_t)stream>>>(*a);
   return rl_check_launch("conv1d_fwd_kernel");
 }
@@ -640,6 +644,7 @@ extern "C" int ralenet_conv1d_bwd(const rl_conv_bwd_args* a, void* stream) {
   if (int rc = conv_check(a->B, a->L, a->Cin, a->Cout, a->K, &smem, true)) return rc;
   RL_REQUIRE(a->dy && a->x && a->w, RL_ERR_NULL, "conv1d_bwd: NULL tensor");
   if (int rc = rl_set_smem(conv1d_bwd_kernel, smem)) return rc;
+  rl_prof_pre((cudaStream_t)stream);
   conv1d_bwd_kernel<<<a->B, RL_NT, smem, (cudaStream_t)stream>>>(*a);
   return rl_check_launch("conv1d_bwd_kernel");
 }
@@ -654,6 +659,7 @@ extern "C" int ralenet_adam(float* p, const float* g, float* m, float* v, int64_
   const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
   const int64_t nthreads = (n + 3) / 4;
   const int blocks = (int)((nthreads + RL_NT - 1) / RL_NT);
+  rl_prof_pre((cudaStream_t)stream);
   adam_kernel<<<blocks, RL_NT, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2s, gscale,
                                                           nullptr);
   return rl_check_launch("adam_kernel");
@@ -668,10 +674,12 @@ extern "C" int ralenet_adam_dev(float* p, const float* g, float* m, float* v, in
   RL_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0, RL_ERR_SHAPE,
              "adam_dev: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  rl_prof_pre(st);
   step_inc_kernel<<<1, 1, 0, st>>>(step_dev);
   if (int rc = rl_check_launch("step_inc_kernel")) return rc;
   const int64_t nthreads = (n + 3) / 4;
   const int blocks = (int)((nthreads + RL_NT - 1) / RL_NT);
+  rl_prof_pre(st);
   adam_kernel<<<blocks, RL_NT, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, 1.f, 1.f, gscale, step_dev);
   return rl_check_launch("adam_kernel");
 }

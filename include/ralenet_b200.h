@@ -314,6 +314,21 @@ int ralenet_net_bwd(const rl_net_cfg* cfg, const rl_net_ptrs* P, const rl_net_pt
 int ralenet_net_bwd_stem(const rl_net_cfg* cfg, const rl_net_ptrs* P, const rl_net_ptrs* G,
                          const float* x, float* dx, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Record <-> window pipeline for long recordings (inference).  The reference cuts records into 256-sample
+ * windows on the host (local_utils/local_utils.py:47-65, 116-130) after per-lead z-normalisation (np_norm,
+ * :261-266) and never stitches them back.  x, y: [R][C][T] channels-first records; win: [R*nper][C][W] with
+ * nper = (T - W)/stride + 1 full windows per record; stats: [R*C][2] = (mean, 1/std) or NULL (no normalisation).
+ * scatter averages overlapping windows (deterministic gather form), undoes the normalisation, and passes
+ * samples not covered by a full window through from x.
+ * ------------------------------------------------------------------------------------------ */
+int ralenet_record_stats(const float* x, int32_t RC, int64_t T, float* stats, void* stream);
+int32_t ralenet_windows_per_record(int64_t T, int32_t W, int32_t stride);
+int ralenet_window_gather(const float* x, const float* stats, float* win, int32_t R, int32_t C, int64_t T,
+                          int32_t W, int32_t stride, void* stream);
+int ralenet_window_scatter(const float* win, const float* x, const float* stats, float* y, int32_t R, int32_t C,
+                           int64_t T, int32_t W, int32_t stride, void* stream);
+
 /* Weight-gradient GEMM over the token dimension (used by every *_bwd above; exported for benchmarks):
  *   dW[n*K + k] += sum_m dY[m*ldy + n] * X[m*ldx + k],   db[n] += sum_m dY[m*ldy + n]   (db may be NULL) */
 int ralenet_wgrad(const float* dY, int32_t ldy, const float* X, int32_t ldx, int32_t M, int32_t N, int32_t K,

@@ -568,3 +568,35 @@ def adam_step(param: Tensor, grad: Tensor, m: Tensor, v: Tensor, step: int,
 def trainable_keys(sd: Dict[str, Tensor]) -> List[str]:
     return [k for k, v in sd.items() if v.dtype.is_floating_point
             and not k.endswith("running_mean") and not k.endswith("running_var")]
+
+
+# ----------------------------------------------------------------------------------------
+# record <-> window pipeline (local_utils/local_utils.py:47-65, 116-130, 261-266)
+# ----------------------------------------------------------------------------------------
+def records_to_windows(x: Tensor, window: int = 256, stride: int = 256, znorm: bool = True):
+    """x: (R, C, T).  Per-lead z-normalisation like np_norm ((x - mean) / std, population std), then the
+    reference's cut `signal[i:i+window]` for i in range(0, T - window + 1, stride).  Returns windows
+    (R*nper, C, window) and (mean, std) of shape (R, C, 1)."""
+    R, C, T = x.shape
+    mean = x.mean(-1, keepdim=True) if znorm else torch.zeros(R, C, 1, dtype=x.dtype)
+    std = x.std(-1, unbiased=False, keepdim=True) if znorm else torch.ones(R, C, 1, dtype=x.dtype)
+    xn = (x - mean) / std
+    nper = (T - window) // stride + 1
+    win = torch.stack([xn[:, :, w * stride:w * stride + window] for w in range(nper)], 1)   # (R, nper, C, W)
+    return win.reshape(R * nper, C, window), (mean, std)
+
+
+def windows_to_records(win: Tensor, x: Tensor, stats, stride: int = 256) -> Tensor:
+    """overlap-add average of the windows, de-normalised; samples not covered by a full window come from x."""
+    R, C, T = x.shape
+    window = win.shape[-1]
+    nper = (T - window) // stride + 1
+    w4 = win.reshape(R, nper, C, window)
+    acc = torch.zeros_like(x)
+    cnt = torch.zeros(T, dtype=x.dtype)
+    for w in range(nper):
+        acc[:, :, w * stride:w * stride + window] += w4[:, w]
+        cnt[w * stride:w * stride + window] += 1
+    mean, std = stats
+    y = torch.where(cnt > 0, acc / cnt.clamp(min=1) * std + mean, x)
+    return y

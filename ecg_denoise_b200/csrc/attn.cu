@@ -7,11 +7,12 @@
 //
 // A window is L tokens x C channels with L*C = 2048 (4096 for 512-sample windows), head_dim 4, so the
 // whole window (x, q, k, v) lives in shared memory and the L x L logits are never materialised:
-// each thread owns one (head, query) row and streams the keys with an online softmax.  The R-wave
-// bias is added from its (2W-1) x H table on the central W x W block only.
+// each warp owns (head, 16-query tile) items and streams the keys through tensor-core MMAs with an online softmax
+// (attn_core.cuh).  The R-wave bias is added from its (2W-1) x H table on the central W x W block only.
 #define RL_NT 512        // 16 warps per window: the benchmark batch (256 windows on 148 SMs) needs the parallelism
 #define RL_MINB 2
 #include "common.cuh"
+#include "attn_core.cuh"
 
 namespace {
 
@@ -80,50 +81,9 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_kernel(const rl_attn_
     copy_rows_s2g(a.v + woff, sv, LDC, L, C);
   }
 
-  // 3. attention core: one (head, query) row per thread, online softmax in the log2 domain.
-  //    o overwrites q in place (only the owner thread ever reads q[i, 4h:4h+4]).
-  const float qs = 0.5f * RL_LOG2E;                  // head_dim^-0.5 (transformer.py:278) * log2(e)
-  for (int item = tid; item < H * L; item += RL_NT) {
-    const int i = item % L, h = item / L;
-    float4 q4 = *reinterpret_cast<const float4*>(sq + i * LDC + 4 * h);
-    q4.x *= qs; q4.y *= qs; q4.z *= qs; q4.w *= qs;
-    const bool central = (W > 0) && ((unsigned)(i - c0) < (unsigned)W);
-    float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-    const float* kp = sk + 4 * h;
-    const float* vp = sv + 4 * h;
-    for (int j0 = 0; j0 < L; j0 += 8) {
-      float s[8];
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const float4 k4 = *reinterpret_cast<const float4*>(kp + (j0 + jj) * LDC);
-        s[jj] = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
-      }
-      if (central) {
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int j = j0 + jj;
-          if ((unsigned)(j - c0) < (unsigned)W) s[jj] += stab[(i - j + W - 1) * H + h];
-        }
-      }
-      float cm = s[0];
-#pragma unroll
-      for (int jj = 1; jj < 8; ++jj) cm = fmaxf(cm, s[jj]);
-      const float mn = fmaxf(m, cm);
-      const float corr = exp2f(m - mn);
-      l *= corr; o0 *= corr; o1 *= corr; o2 *= corr; o3 *= corr;
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const float p = exp2f(s[jj] - mn);
-        const float4 v4 = *reinterpret_cast<const float4*>(vp + (j0 + jj) * LDC);
-        l += p;
-        o0 = fmaf(p, v4.x, o0); o1 = fmaf(p, v4.y, o1); o2 = fmaf(p, v4.z, o2); o3 = fmaf(p, v4.w, o3);
-      }
-      m = mn;
-    }
-    const float inv = 1.0f / l;
-    *reinterpret_cast<float4*>(sq + i * LDC + 4 * h) = make_float4(o0 * inv, o1 * inv, o2 * inv, o3 * inv);
-    if (a.lse) a.lse[(size_t)blockIdx.x * H * L + item] = m + log2f(l);
-  }
+  // 3. attention core on the tensor cores (attn_core.cuh): one (head, 16-query tile) per warp, online softmax in
+  //    the log2 domain; o overwrites q in place.
+  attn_core_fwd<C, L>(sq, sk, sv, stab, W, c0, a.lse ? a.lse + (size_t)blockIdx.x * H * L : nullptr);
   __syncthreads();
   if (a.o) copy_rows_s2g(a.o + woff, sq, LDC, L, C);
 
@@ -213,57 +173,11 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   if (FW) cta_wgrad<C, C, L>(sdq, LDC, sdk, LDC, a.d_wp, a.d_bp);          // dWp = g^T o,  dbp = sum g
   if (FW) __syncthreads();
 
-  const float qs = 0.5f * RL_LOG2E;
-  // 4a. dq: one (head, query) row per thread
-  for (int item = tid; item < H * L; item += RL_NT) {
-    const int i = item % L, h = item / L;
-    float4 q4 = *reinterpret_cast<const float4*>(sq + i * LDC + 4 * h);
-    q4.x *= qs; q4.y *= qs; q4.z *= qs; q4.w *= qs;
-    const float4 d4 = *reinterpret_cast<const float4*>(sdo + i * LDC + 4 * h);
-    const float Di = sD[item], lse = sLse[item];
-    const bool central = (W > 0) && ((unsigned)(i - c0) < (unsigned)W);
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    const float* kp = sk + 4 * h;
-    const float* vp = sv + 4 * h;
-    for (int j = 0; j < L; ++j) {
-      const float4 k4 = *reinterpret_cast<const float4*>(kp + j * LDC);
-      const float4 v4 = *reinterpret_cast<const float4*>(vp + j * LDC);
-      float s = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
-      const bool cpair = central && ((unsigned)(j - c0) < (unsigned)W);
-      if (cpair) s += stab[(i - j + W - 1) * H + h];
-      const float p = exp2f(s - lse);
-      const float dp = d4.x * v4.x + d4.y * v4.y + d4.z * v4.z + d4.w * v4.w;
-      const float ds = p * (dp - Di);
-      a0 = fmaf(ds, k4.x, a0); a1 = fmaf(ds, k4.y, a1); a2 = fmaf(ds, k4.z, a2); a3 = fmaf(ds, k4.w, a3);
-      if (cpair && a.d_table) atomicAdd(&stabg[(i - j + W - 1) * H + h], ds);
-    }
-    *reinterpret_cast<float4*>(sdq + i * LDC + 4 * h) = make_float4(0.5f * a0, 0.5f * a1, 0.5f * a2, 0.5f * a3);
-  }
-  // 4b. dk, dv: one (head, key) column per thread (sdk held o, last read in step 3 before a barrier)
-  for (int item = tid; item < H * L; item += RL_NT) {
-    const int j = item % L, h = item / L;
-    const float4 k4 = *reinterpret_cast<const float4*>(sk + j * LDC + 4 * h);
-    const float4 v4 = *reinterpret_cast<const float4*>(sv + j * LDC + 4 * h);
-    const bool centralj = (W > 0) && ((unsigned)(j - c0) < (unsigned)W);
-    float k0a = 0.f, k1a = 0.f, k2a = 0.f, k3a = 0.f, v0a = 0.f, v1a = 0.f, v2a = 0.f, v3a = 0.f;
-    const float* qp = sq + 4 * h;
-    const float* dp_ = sdo + 4 * h;
-    const float* Dp = sD + h * L;
-    const float* Lp = sLse + h * L;
-    for (int i = 0; i < L; ++i) {
-      const float4 q4 = *reinterpret_cast<const float4*>(qp + i * LDC);
-      const float4 d4 = *reinterpret_cast<const float4*>(dp_ + i * LDC);
-      float s = qs * (q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w);
-      if (centralj && ((unsigned)(i - c0) < (unsigned)W)) s += stab[(i - j + W - 1) * H + h];
-      const float p = exp2f(s - Lp[i]);
-      v0a = fmaf(p, d4.x, v0a); v1a = fmaf(p, d4.y, v1a); v2a = fmaf(p, d4.z, v2a); v3a = fmaf(p, d4.w, v3a);
-      const float dpv = d4.x * v4.x + d4.y * v4.y + d4.z * v4.z + d4.w * v4.w;
-      const float ds = p * (dpv - Dp[i]);
-      k0a = fmaf(ds, q4.x, k0a); k1a = fmaf(ds, q4.y, k1a); k2a = fmaf(ds, q4.z, k2a); k3a = fmaf(ds, q4.w, k3a);
-    }
-    *reinterpret_cast<float4*>(sdk + j * LDC + 4 * h) = make_float4(0.5f * k0a, 0.5f * k1a, 0.5f * k2a, 0.5f * k3a);
-    *reinterpret_cast<float4*>(sdv + j * LDC + 4 * h) = make_float4(v0a, v1a, v2a, v3a);
-  }
+  // 4. attention core backward on the tensor cores (attn_core.cuh): a query-major pass for dq (+ the R-wave table
+  //    gradient) and a key-major pass for dk, dv; p is recomputed from the saved log-sum-exp.
+  //    (sdk held o, last read in step 3 before a barrier)
+  attn_core_bwd_dq<C, L>(sq, sk, sv, sdo, sD, sLse, sdq, stab, stabg, a.d_table != nullptr, W, c0);
+  attn_core_bwd_dkv<C, L>(sq, sk, sv, sdo, sD, sLse, sdk, sdv, stab, W, c0);
   __syncthreads();
 
   // 5. dqkv scratch [t][dq | dk | dv] for the weight-gradient GEMMs

@@ -12,6 +12,8 @@
 #include "common.cuh"
 
 // cluster kernels for the wide stages (ffn_cluster.cu); return 1 when the shape/mode is not handled there
+int rl_ffn_fwd_umma(const rl_ffn_fwd_args* a, cudaStream_t st);      // tcgen05 kernels (ffn_umma.cu)
+int rl_ffn_bwd_umma(const rl_ffn_bwd_args* a, cudaStream_t st);
 int rl_ffn_fwd_cluster(const rl_ffn_fwd_args* a, cudaStream_t st);
 int rl_ffn_bwd_cluster(const rl_ffn_bwd_args* a, cudaStream_t st);
 
@@ -366,7 +368,9 @@ extern "C" int ralenet_ffn_fwd(const rl_ffn_fwd_args* a, void* stream) {
   RL_REQUIRE(a->le_mode == RL_LE_NONE || a->lew, RL_ERR_NULL, "ffn_fwd: le_mode needs lew");
   cudaStream_t st = (cudaStream_t)stream;
   {
-    const int rc = rl_ffn_fwd_cluster(a, st);
+    int rc = rl_ffn_fwd_umma(a, st);
+    if (rc <= 0) return rc;
+    rc = rl_ffn_fwd_cluster(a, st);
     if (rc <= 0) return rc;
   }
   switch (a->C) {
@@ -388,7 +392,9 @@ extern "C" int ralenet_ffn_bwd(const rl_ffn_bwd_args* a, void* stream) {
   RL_REQUIRE(a->le_mode == RL_LE_NONE || a->lew, RL_ERR_NULL, "ffn_bwd: le_mode needs lew");
   RL_REQUIRE(!a->d_ln_w == !a->d_ln_b, RL_ERR_NULL, "ffn_bwd: d_ln_w/d_ln_b must be both set or both NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = rl_ffn_bwd_cluster(a, st);
+  int rc = rl_ffn_bwd_umma(a, st);
+  if (rc < 0) return rc;
+  if (rc == 1) rc = rl_ffn_bwd_cluster(a, st);
   if (rc < 0) return rc;
   if (rc == 1) switch (a->C) {
     case 8: rc = launch_bwd<8>(a, st); break;

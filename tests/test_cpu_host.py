@@ -203,3 +203,28 @@ def test_data_parallel_equals_single_process_gloo_world2():
     assert abs(loss - loss_ref.item()) < 1e-12
     assert np.allclose(flat, flat_ref, rtol=1e-9, atol=1e-12)
     assert np.allclose(rm, new_stats[0].numpy(), rtol=1e-12) and np.allclose(rv, new_stats[1].numpy(), rtol=1e-12)
+
+
+def test_kernel_gelu_formula_matches_exact_erf_gelu():
+    """common.cuh::gelu_parts replaces libdevice erff by the Abramowitz-Stegun 7.1.26 tail form.  Restated here in
+    numpy float32, operation by operation, and held against the fp64 nn.GELU() (model/transformer.py:138, exact erf)
+    and its derivative: absolute error below 1e-6 on [-12, 12] -- the level of the erff-based fp32 evaluation."""
+    from scipy.special import erf
+    f = np.float32
+    x = np.linspace(-12, 12, 400001).astype(f)
+    z = np.abs(x) * f(0.70710678118654752)
+    t = (f(1) / (f(0.3275911) * z + f(1))).astype(f)
+    e = np.exp2((x * x * f(-0.72134752044448170)).astype(f)).astype(f)
+    q = (f(0.5 * 1.061405429) * t + f(0.5 * -1.453152027)).astype(f)
+    for coef in (0.5 * 1.421413741, 0.5 * -0.284496736, 0.5 * 0.254829592):
+        q = (q * t + f(coef)).astype(f)
+    q = (q * t * e).astype(f)
+    cdf = np.where(x < 0, q, f(1) - q).astype(f)
+    g = (x * cdf).astype(f)
+    dg = (x * e * f(0.3989422804014327) + cdf).astype(f)
+    xd = x.astype(np.float64)
+    cdf64 = 0.5 * (1 + erf(xd / np.sqrt(2)))
+    g64 = xd * cdf64
+    dg64 = cdf64 + xd * np.exp(-0.5 * xd * xd) / np.sqrt(2 * np.pi)
+    assert np.abs(g - g64).max() < 1e-6
+    assert np.abs(dg - dg64).max() < 1e-6

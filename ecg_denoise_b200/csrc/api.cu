@@ -33,6 +33,8 @@ struct Prof {
 Prof g_prof;
 }  // namespace
 
+bool rl_prof_active() { return g_prof.on; }
+
 void rl_prof_pre(cudaStream_t st) {
   if (g_prof.on && g_prof.n < kMaxProf && st == g_prof.stream) {
     cudaEventRecord(g_prof.pre[g_prof.n], st);

@@ -302,7 +302,8 @@ extern "C" int ralenet_attn_fwd(const rl_attn_fwd_args* a, void* stream) {
   return RL_ERR_SHAPE;
 }
 
-extern "C" int ralenet_attn_bwd(const rl_attn_bwd_args* a, void* stream) {
+// the data-gradient kernel (also writes the dqkv / u scratch of the weight gradients)
+int rl_attn_bwd_main(const rl_attn_bwd_args* a, cudaStream_t st) {
   RL_REQUIRE(a, RL_ERR_NULL, "attn_bwd: args is NULL");
   if (int rc = check_shape(a->B, a->L, a->C, a->H, a->W, a->c0)) return rc;
   RL_REQUIRE(a->g && a->x && a->wq && a->wkv && a->wp && a->q && a->k && a->v && a->o && a->lse && a->dx && a->dqkv &&
@@ -311,20 +312,33 @@ extern "C" int ralenet_attn_bwd(const rl_attn_bwd_args* a, void* stream) {
   RL_REQUIRE(!(a->flags & RL_F_PRENORM) || (a->pe && a->ln_w && a->ln_b), RL_ERR_NULL, "attn_bwd: prenorm needs pe/ln");
   RL_REQUIRE(a->W == 0 || a->table, RL_ERR_NULL, "attn_bwd: W>0 needs table");
   RL_REQUIRE(!a->d_ln_w == !a->d_ln_b, RL_ERR_NULL, "attn_bwd: d_ln_w/d_ln_b must be both set or both NULL");
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc = RL_ERR_SHAPE;
   switch (a->C) {
-    case 8: rc = launch_bwd<8>(a, st); break;
-    case 16: rc = launch_bwd<16>(a, st); break;
-    case 32: rc = launch_bwd<32>(a, st); break;
-    case 64: rc = launch_bwd<64>(a, st); break;
-    case 128: rc = launch_bwd<128>(a, st); break;
+    case 8: return launch_bwd<8>(a, st);
+    case 16: return launch_bwd<16>(a, st);
+    case 32: return launch_bwd<32>(a, st);
+    case 64: return launch_bwd<64>(a, st);
+    case 128: return launch_bwd<128>(a, st);
   }
-  if (rc) return rc;
+  return RL_ERR_SHAPE;
+}
+
+// true when the weight gradients of this shape are a separate launch (rl_attn_bwd_wgrad)
+bool rl_attn_bwd_has_wgrad(const rl_attn_bwd_args* a) {
+  return a->C > 16 && (a->d_wp || a->d_wq || a->d_wkv);
+}
+
+// weight gradients from (g, o) and the scratch tensors; may run on another stream once the main kernel is done
+int rl_attn_bwd_wgrad(const rl_attn_bwd_args* a, cudaStream_t st) {
   const int M = a->B * a->L, C = a->C;
   if (C <= 16) return RL_OK;        // narrow stages accumulate their weight gradients inside the kernel
   const RlWgradDesc d[3] = {{a->g, C, a->o, C, C, C, a->d_wp, a->d_bp},
                             {a->dqkv, 3 * C, a->u, C, C, C, a->d_wq, a->d_bq},
                             {a->dqkv + C, 3 * C, a->u, C, 2 * C, C, a->d_wkv, a->d_bkv}};
   return rl_launch_wgrad_group(d, 3, M, st);
+}
+
+extern "C" int ralenet_attn_bwd(const rl_attn_bwd_args* a, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = rl_attn_bwd_main(a, st)) return rc;
+  return rl_attn_bwd_wgrad(a, st);
 }

@@ -601,3 +601,13 @@ struct RlWgradDesc {
   const float* dY; int ldy; const float* X; int ldx; int N, K; float* dW; float* db;
 };
 int rl_launch_wgrad_group(const RlWgradDesc* d, int n, int M, cudaStream_t st);
+
+// backward halves split into the data-gradient kernel and the weight-gradient GEMMs (net.cu runs the latter on a
+// side stream, off the critical path of the backward chain)
+int rl_attn_bwd_main(const rl_attn_bwd_args* a, cudaStream_t st);
+int rl_attn_bwd_wgrad(const rl_attn_bwd_args* a, cudaStream_t st);
+bool rl_attn_bwd_has_wgrad(const rl_attn_bwd_args* a);
+int rl_ffn_bwd_main(const rl_ffn_bwd_args* a, cudaStream_t st);
+int rl_ffn_bwd_wgrad(const rl_ffn_bwd_args* a, cudaStream_t st);
+bool rl_ffn_bwd_has_wgrad(const rl_ffn_bwd_args* a);
+bool rl_prof_active();                 // per-launch profiling is on: keep every launch on the profiled stream

@@ -383,7 +383,7 @@ extern "C" int ralenet_ffn_fwd(const rl_ffn_fwd_args* a, void* stream) {
   return RL_ERR_SHAPE;
 }
 
-extern "C" int ralenet_ffn_bwd(const rl_ffn_bwd_args* a, void* stream) {
+int rl_ffn_bwd_main(const rl_ffn_bwd_args* a, cudaStream_t st) {
   RL_REQUIRE(a, RL_ERR_NULL, "ffn_bwd: args is NULL");
   if (int rc = check_shape(a->B, a->L, a->C, a->le_mode)) return rc;
   RL_REQUIRE(a->g && a->x && a->w1 && a->w2 && a->h && a->dx && a->dh && a->g2 && a->u, RL_ERR_NULL,
@@ -391,7 +391,6 @@ extern "C" int ralenet_ffn_bwd(const rl_ffn_bwd_args* a, void* stream) {
   RL_REQUIRE(!(a->flags & RL_F_PRENORM) || (a->ln_w && a->ln_b), RL_ERR_NULL, "ffn_bwd: prenorm needs ln");
   RL_REQUIRE(a->le_mode == RL_LE_NONE || a->lew, RL_ERR_NULL, "ffn_bwd: le_mode needs lew");
   RL_REQUIRE(!a->d_ln_w == !a->d_ln_b, RL_ERR_NULL, "ffn_bwd: d_ln_w/d_ln_b must be both set or both NULL");
-  cudaStream_t st = (cudaStream_t)stream;
   int rc = rl_ffn_bwd_umma(a, st);
   if (rc < 0) return rc;
   if (rc == 1) rc = rl_ffn_bwd_cluster(a, st);
@@ -403,10 +402,22 @@ extern "C" int ralenet_ffn_bwd(const rl_ffn_bwd_args* a, void* stream) {
     case 64: rc = launch_bwd<64>(a, st); break;
     case 128: rc = launch_bwd<128>(a, st); break;
   }
-  if (rc) return rc;
+  return rc;
+}
+
+bool rl_ffn_bwd_has_wgrad(const rl_ffn_bwd_args* a) { return a->C > 16 && (a->d_w1 || a->d_w2); }
+
+// weight gradients from (g, g2) and (dh, u); may run on another stream once the main kernel is done
+int rl_ffn_bwd_wgrad(const rl_ffn_bwd_args* a, cudaStream_t st) {
   const int M = a->B * a->L, C = a->C;
   if (C <= 16) return RL_OK;        // narrow stages accumulate their weight gradients inside the kernel
   const RlWgradDesc d[2] = {{a->g, C, a->g2, 4 * C, C, 4 * C, a->d_w2, a->d_b2},
                             {a->dh, 4 * C, a->u, C, 4 * C, C, a->d_w1, a->d_b1}};
   return rl_launch_wgrad_group(d, 2, M, st);
+}
+
+extern "C" int ralenet_ffn_bwd(const rl_ffn_bwd_args* a, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = rl_ffn_bwd_main(a, st)) return rc;
+  return rl_ffn_bwd_wgrad(a, st);
 }

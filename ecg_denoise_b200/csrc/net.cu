@@ -28,7 +28,9 @@ struct Ws {
   float* x0;
   BlockWs blk[RL_NBLOCKS];
   float *pm_out[4], *pm_u[4], *ps_out[4], *ps_u[4];
-  float *dqkv, *u, *dh, *g2, *gsum, *gA, *gB, *gskip[5], *gx0, *gfirst, *partials;
+  // two sets of weight-gradient scratch (alternating per block) and four rotating gradient buffers: the
+  // weight-gradient GEMMs run on a side stream up to three kernels behind the data-gradient chain
+  float *dqkv[2], *ua[2], *dh[2], *g2[2], *uf[2], *gsum, *grot[4], *gskip[5], *gx0, *gfirst, *partials;
   float *ping, *pong;   // inference only
   size_t floats;
 };
@@ -52,8 +54,11 @@ Ws carve(float* base, int B, int L0, int save) {
       b.lse = take(N / 4); b.h = take(4 * N);
     }
     for (int j = 0; j < 4; ++j) { w.pm_u[j] = take(N); w.ps_out[j] = take(N); w.ps_u[j] = take(N); }
-    w.dqkv = take(3 * N); w.u = take(N); w.dh = take(4 * N); w.g2 = take(4 * N); w.gsum = take(N);
-    w.gA = take(N); w.gB = take(N);
+    for (int p = 0; p < 2; ++p) {
+      w.dqkv[p] = take(3 * N); w.ua[p] = take(N); w.dh[p] = take(4 * N); w.g2[p] = take(4 * N); w.uf[p] = take(N);
+    }
+    w.gsum = take(N);
+    for (int p = 0; p < 4; ++p) w.grot[p] = take(N);
     w.gskip[0] = nullptr;
     for (int j = 1; j <= 4; ++j) w.gskip[j] = take(N);
     w.gx0 = take(N);
@@ -77,6 +82,34 @@ int check_cfg(const rl_net_cfg* cfg, const rl_net_ptrs* P) {
              "net: workspace missing or too small (%llu bytes given)", (unsigned long long)cfg->ws_bytes);
   RL_REQUIRE(cfg->running_mean && cfg->running_var && cfg->bn_stats, RL_ERR_NULL, "net: BN buffers missing");
   for (int s = 0; s < 5; ++s) RL_REQUIRE(cfg->pe[s], RL_ERR_NULL, "net: positional table %d missing", s);
+  return RL_OK;
+}
+
+// Side stream for the weight-gradient GEMMs of the backward pass.  One context per host thread (backward runs on
+// autograd threads), created on first use; events carry no timing.  Under stream capture the fork / join below
+// becomes parallel branches of the captured graph.
+struct SideCtx {
+  bool ready = false;
+  int dev = -1;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_main[4], ev_side[4];
+};
+thread_local SideCtx g_side;
+
+int side_ctx(SideCtx** out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!g_side.ready || g_side.dev != dev) {
+    cudaError_t e = cudaStreamCreateWithFlags(&g_side.side, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) {
+      e = cudaEventCreateWithFlags(&g_side.ev_main[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_side.ev_side[i], cudaEventDisableTiming);
+    }
+    RL_REQUIRE(e == cudaSuccess, RL_ERR_CUDA, "net_bwd: side stream setup failed: %s", cudaGetErrorString(e));
+    g_side.ready = true;
+    g_side.dev = dev;
+  }
+  *out = &g_side;
   return RL_OK;
 }
 
@@ -207,13 +240,42 @@ extern "C" int ralenet_net_bwd(const rl_net_cfg* cfg, const rl_net_ptrs* P, cons
     if ((rc = ralenet_head_bwd(&ha, stream))) return rc;
   }
   const float* g = w.gx0;          // gradient w.r.t. the output of the piece about to be differentiated
-  float* pp[2] = {w.gA, w.gB};
-  int pi = 0;
-  auto next_g = [&]() { float* p = pp[pi]; pi ^= 1; return p; };
+  // Main chain: patch / feed-forward / attention data-gradient kernels, numbered n = 0, 1, ...; kernel n writes
+  // its data gradient to the rotating buffer grot[n % 4] (unless it has a dedicated destination) and its
+  // weight-gradient scratch to set (block & 1).  The weight-gradient GEMMs of kernel n are forked to the side
+  // stream; before kernel n starts, the main stream waits for the GEMMs of kernel n - 3 (and, the side stream
+  // being in-order, of every earlier one), which are the last readers of everything kernel n overwrites.
+  cudaStream_t st_main = (cudaStream_t)stream;
+  SideCtx* sc = nullptr;
+  const bool use_side = !rl_prof_active();
+  if (use_side)
+    if ((rc = side_ctx(&sc))) return rc;
+  int n = 0;
+  int side_idx[4] = {-1, -1, -1, -1};
+  int last_side = -1;
+  auto before_main = [&]() {
+    const int slot = (n + 1) & 3;                 // == (n - 3) mod 4
+    if (use_side && n >= 3 && side_idx[slot] == n - 3) cudaStreamWaitEvent(st_main, sc->ev_side[slot], 0);
+  };
+  auto rot = [&]() { return w.grot[n & 3]; };
+  // fork the weight gradients of main kernel n; `launch` enqueues them on the given stream
+  auto fork_wgrad = [&](bool has, auto launch) -> int {
+    if (!has) return RL_OK;
+    if (!use_side) return launch(st_main);
+    const int slot = n & 3;
+    cudaEventRecord(sc->ev_main[slot], st_main);
+    cudaStreamWaitEvent(sc->side, sc->ev_main[slot], 0);
+    if (int r2 = launch(sc->side)) return r2;
+    cudaEventRecord(sc->ev_side[slot], sc->side);
+    side_idx[slot] = n;
+    last_side = slot;
+    return RL_OK;
+  };
   for (int i = RL_NBLOCKS - 1; i >= 0; --i) {
     const int s = kBlocks[i].stage, rwi = kBlocks[i].rw;
     const int C = 8 << s, L = L0 >> s, H = 2 << s;
     const int layer = i / 2;
+    const int set = i & 1;
     float* const* bp = P->blk[i];
     float* const* bg = G->blk[i];
     const float* g_extra_for_pm = nullptr;
@@ -224,9 +286,11 @@ extern "C" int ralenet_net_bwd(const rl_net_cfg* cfg, const rl_net_ptrs* P, cons
         rl_patch_bwd_args pa = {};
         pa.B = B; pa.L = L; pa.C = C; pa.mode = 1;
         pa.g = g; pa.g2 = nullptr; pa.x = w.blk[i].y; pa.ln_w = P->ps[j][1]; pa.w = P->ps[j][0]; pa.u = w.ps_u[j];
-        pa.dx = next_g(); pa.gsum = nullptr;
+        before_main();
+        pa.dx = rot(); pa.gsum = nullptr;
         pa.d_w = G->ps[j][0]; pa.d_ln_w = G->ps[j][1]; pa.d_ln_b = G->ps[j][2];
         if ((rc = ralenet_patch_bwd(&pa, stream))) return rc;
+        ++n;
         g = pa.dx;
       } else if (layer < 4) {
         g_extra_for_pm = w.gskip[layer + 1];       // skip consumer (ps / x_mid) gradient of pm_out[layer]
@@ -234,9 +298,11 @@ extern "C" int ralenet_net_bwd(const rl_net_cfg* cfg, const rl_net_ptrs* P, cons
         pa.B = B; pa.L = L; pa.C = C; pa.mode = 0;
         pa.g = g; pa.g2 = g_extra_for_pm; pa.x = w.blk[i].y; pa.ln_w = P->pm[layer][1]; pa.w = P->pm[layer][0];
         pa.u = w.pm_u[layer];
-        pa.dx = next_g(); pa.gsum = w.gsum;
+        before_main();
+        pa.dx = rot(); pa.gsum = w.gsum;
         pa.d_w = G->pm[layer][0]; pa.d_ln_w = G->pm[layer][1]; pa.d_ln_b = G->pm[layer][2];
         if ((rc = ralenet_patch_bwd(&pa, stream))) return rc;
+        ++n;
         g = pa.dx;
       }
       // layer 4 ("transformer"): y9 = blk9(...) + x4; the x4 part is g itself, kept in gskip[4] below
@@ -246,10 +312,14 @@ extern "C" int ralenet_net_bwd(const rl_net_cfg* cfg, const rl_net_ptrs* P, cons
     fa.B = B; fa.L = L; fa.C = C; fa.le_mode = cfg->le_mode; fa.flags = RL_F_PRENORM | RL_F_RESIDUAL;
     fa.g = g; fa.x = w.blk[i].xa; fa.ln_w = bp[RL_BLK_LN2W]; fa.ln_b = bp[RL_BLK_LN2B];
     fa.w1 = bp[RL_BLK_W1]; fa.w2 = bp[RL_BLK_W2]; fa.lew = bp[RL_BLK_LEW]; fa.h = w.blk[i].h;
-    fa.dx = next_g(); fa.dh = w.dh; fa.g2 = w.g2; fa.u = w.u;
+    before_main();
+    fa.dx = rot(); fa.dh = w.dh[set]; fa.g2 = w.g2[set]; fa.u = w.uf[set];
     fa.d_ln_w = bg[RL_BLK_LN2W]; fa.d_ln_b = bg[RL_BLK_LN2B]; fa.d_w1 = bg[RL_BLK_W1]; fa.d_b1 = bg[RL_BLK_B1];
     fa.d_w2 = bg[RL_BLK_W2]; fa.d_b2 = bg[RL_BLK_B2]; fa.d_lew = bg[RL_BLK_LEW];
-    if ((rc = ralenet_ffn_bwd(&fa, stream))) return rc;
+    if ((rc = rl_ffn_bwd_main(&fa, st_main))) return rc;
+    if ((rc = fork_wgrad(rl_ffn_bwd_has_wgrad(&fa), [&](cudaStream_t q) { return rl_ffn_bwd_wgrad(&fa, q); })))
+      return rc;
+    ++n;
     g = fa.dx;
 
     rl_attn_bwd_args aa = {};
@@ -264,18 +334,23 @@ extern "C" int ralenet_net_bwd(const rl_net_cfg* cfg, const rl_net_ptrs* P, cons
     aa.q = w.blk[i].q; aa.k = w.blk[i].k; aa.v = w.blk[i].v; aa.o = w.blk[i].o; aa.lse = w.blk[i].lse;
     // where does dL/d(block input) go?  first block of an up layer (or of the mid layers) produces a
     // gradient that is also the U-skip gradient of a pm output, so it gets a dedicated buffer.
+    before_main();
     float* dst;
     if (i % 2 == 0 && layer >= 5) dst = w.gskip[9 - layer];       // layer 5 -> gskip[4] (x_mid), 6 -> [3], 7 -> [2], 8 -> [1]
     else if (i == 0) dst = w.gfirst;                              // dL/d(stem output) through the blocks
-    else dst = next_g();
-    aa.dx = dst; aa.dqkv = w.dqkv; aa.u = w.u;
+    else dst = rot();
+    aa.dx = dst; aa.dqkv = w.dqkv[set]; aa.u = w.ua[set];
     aa.d_ln_w = bg[RL_BLK_LN1W]; aa.d_ln_b = bg[RL_BLK_LN1B];
     aa.d_wq = bg[RL_BLK_WQ]; aa.d_bq = bg[RL_BLK_BQ]; aa.d_wkv = bg[RL_BLK_WKV]; aa.d_bkv = bg[RL_BLK_BKV];
     aa.d_wp = bg[RL_BLK_WP]; aa.d_bp = bg[RL_BLK_BP];
     aa.d_table = has_rw ? G->table[rwi] : nullptr;
-    if ((rc = ralenet_attn_bwd(&aa, stream))) return rc;
+    if ((rc = rl_attn_bwd_main(&aa, st_main))) return rc;
+    if ((rc = fork_wgrad(rl_attn_bwd_has_wgrad(&aa), [&](cudaStream_t q) { return rl_attn_bwd_wgrad(&aa, q); })))
+      return rc;
+    ++n;
     g = dst;
   }
+  if (use_side && last_side >= 0) cudaStreamWaitEvent(st_main, sc->ev_side[last_side], 0);   // join
   // g = dL/d(x0) through the blocks; the final skip adds gx0 (transformer.py:665)
   rl_stem_bwd_args sb = {};
   sb.B = B; sb.L = L0; sb.training = cfg->training;

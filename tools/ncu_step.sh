@@ -1,0 +1,12 @@
+#!/bin/bash
+# `ncu --set full` of the dominant kernels of one eager training step (source-level), exported as CSV.
+# Run on the GPU box: gpurun -- bash tools/ncu_step.sh <tag>.  A whole-step full capture (131 kernels x 39 passes with a
+# 466 MB workspace to save/restore per pass) takes > 15 min -- do not do that.
+tag=${1:-step}
+mkdir -p gpurun_out
+BENCH="python bench.py --steps 3 --warmup 3 --graph off --no-cpu-baseline --no-profile"
+RX='regex:(attn_bwd_kernel<16|attn_bwd_kernel<8|attn_fwd_kernel<16|attn_fwd_kernel<128|ffn_bwd_kernel<16|ffn_fwd_umma_kernel<128|ffn_bwd_umma_kernel<128|wgrad_group_kernel<64, 32|patch_bwd_kernel<32)'
+timeout 420 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k "$RX" -s 60 -c 14 \
+  -o gpurun_out/${tag}_top $BENCH > gpurun_out/${tag}_ncu.log 2>&1
+ncu -i gpurun_out/${tag}_top.ncu-rep --page raw --csv > gpurun_out/${tag}_top_raw.csv 2>/dev/null
+ls -la gpurun_out | tail -8

@@ -357,8 +357,9 @@ def main():
     ms, ms_e2e = float(t[0]), float(t[1])
 
     # ---- per-kernel timing (roofline pass; un-graphed, events after every launch) ------------------------
+    # (under torch.distributed every rank runs it -- the eager step contains the collectives -- and rank 0 reports)
     roofline, table = None, None
-    if not args.no_profile and rank == 0:
+    if not args.no_profile:
         lib = _lib.load()
         st = torch.cuda.current_stream().cuda_stream
         agg = {}
@@ -399,7 +400,7 @@ def main():
                         "note": "fp32 FFMA (CUDA-core) kernel this round: the honest denominator is the tensor peak "
                                 "the north star names; fp32 FFMA peak on this part is ~72 TFLOP/s",
                         "hbm_algorithmic_GBs": (nbytes / (top[2] * 1e-3) / 1e9) if nbytes else None}
-        if args.dump_kernels:
+        if args.dump_kernels and rank == 0:
             with open(args.dump_kernels, "w") as f:
                 json.dump({"per_step_ms_sum": total / reps, "kernels": [
                     {"label": l, "launches_per_step": c, "avg_ms": a, "ms_per_step": s} for l, c, a, s in table]}, f,

@@ -14,7 +14,9 @@ from typing import Dict
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 HEADER = os.path.join(_ROOT, "include", "ralenet_b200.h")
-LIB_PATH = os.path.join(_HERE, "libralenet_b200.so")
+# RALENET_B200_LIB selects another build of the SAME library (A/B experiments on kernel variants); there is no
+# alternative implementation behind it
+LIB_PATH = os.environ.get("RALENET_B200_LIB") or os.path.join(_HERE, "libralenet_b200.so")
 
 _SCALARS = {
     "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64,

@@ -14,11 +14,23 @@
 #include "common.cuh"
 #include "attn_core.cuh"
 
+RL_TRACE_DEFINE(attn)
+
 namespace {
 
+// weight streams: the wide stages pull their weights through deeper rings of smaller chunks (more loads in flight;
+// a 2-stage ring leaves the L2 latency of every chunk exposed), sized so that two CTAs still fit on an SM
+template <int C>
+struct AttnW {
+  static constexpr int NS = (C >= 64) ? 4 : 2;
+  using Qkv = WStream<3 * C, C, B_NK, NS, STAGE_BUDGET>;
+  using Proj = WStream<C, C, B_NK, NS, (C >= 128) ? STAGE_BUDGET / 2 : STAGE_BUDGET>;
+  using Dgrad = WStream<C, 3 * C, B_KN, NS, (C >= 64) ? STAGE_BUDGET / 2 : STAGE_BUDGET, C>;   // du = [dq|dk|dv] [Wq;Wkv]
+  using DProj = WStream<C, C, B_KN, NS, (C >= 64) ? STAGE_BUDGET / 2 : STAGE_BUDGET>;          // do = g Wp
+};
 template <int C>
 __host__ __device__ constexpr int attn_fwd_swf() {
-  return cmax(WStream<3 * C, C, B_NK>::FLOATS, WStream<C, C, B_NK>::FLOATS);
+  return cmax(AttnW<C>::Qkv::FLOATS, AttnW<C>::Proj::FLOATS);
 }
 template <int C>
 size_t attn_fwd_smem(int L) { return sizeof(float) * (4 * (size_t)L * ld_mk(C) + attn_fwd_swf<C>() + 128); }
@@ -26,8 +38,6 @@ size_t attn_fwd_smem(int L) { return sizeof(float) * (4 * (size_t)L * ld_mk(C) +
 // ---------------------------------------------------------------------------------------------
 template <int C, int WIN>
 __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_kernel(const rl_attn_fwd_args a) {
-  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
-  pdl_trigger();   // let the next kernel get scheduled while this one runs
   extern __shared__ __align__(16) float smem[];
   constexpr int L = 2048 * WIN / C, H = C / RL_HD;
   constexpr int LDC = ld_mk(C);
@@ -38,6 +48,12 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_kernel(const rl_attn_
   float* sv = sk + L * LDC;
   float* sw = sv + L * LDC;
   float* stab = sw + attn_fwd_swf<C>();
+  // the weights are not produced by the preceding kernels of the step: start pulling them before the dependency wait
+  RL_TS(attn, 0);
+  AttnW<C>::Qkv::prefetch(sw, a.wq, C, a.wkv, C);
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
+  RL_TS(attn, 1);
   const int tid = threadIdx.x;
   const size_t woff = (size_t)blockIdx.x * L * C;
   const float* xw = a.x + woff;
@@ -57,12 +73,14 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_kernel(const rl_attn_
   if (W > 0)
     for (int i = tid; i < (2 * W - 1) * H; i += RL_NT) stab[i] = __ldg(a.table + i) * RL_LOG2E;
   __syncthreads();
+  RL_TS(attn, 2);
 
   // 2. [q|k|v] = u [Wq;Wkv]^T + b   (N = 3C, K = C): tensor-core GEMM, weights streamed through sw in K chunks
   {
     MmaTile<L, 3 * C> acc;
     acc.init();
-    WStream<3 * C, C, B_NK>::run(acc, su, LDC, sw, a.wq, C, a.wkv, C);
+    AttnW<C>::Qkv::template run<true>(acc, su, LDC, sw, a.wq, C, a.wkv, C);
+    AttnW<C>::Proj::prefetch(sw, a.wp, C, nullptr, C);        // lands while the attention core runs
     const float* bq = a.bq;
     const float* bkv = a.bkv;
     acc.epilogue([&](int t, int n, float v) {
@@ -75,23 +93,28 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_kernel(const rl_attn_
     });
   }
   __syncthreads();
+  RL_TS(attn, 3);
   if (a.q) {
     copy_rows_s2g(a.q + woff, sq, LDC, L, C);
     copy_rows_s2g(a.k + woff, sk, LDC, L, C);
     copy_rows_s2g(a.v + woff, sv, LDC, L, C);
   }
+  RL_TS(attn, 4);
 
   // 3. attention core on the tensor cores (attn_core.cuh): one (head, 16-query tile) per warp, online softmax in
   //    the log2 domain; o overwrites q in place.
   attn_core_fwd<C, L>(sq, sk, sv, stab, W, c0, a.lse ? a.lse + (size_t)blockIdx.x * H * L : nullptr);
   __syncthreads();
+  RL_TS(attn, 5);
   if (a.o) copy_rows_s2g(a.o + woff, sq, LDC, L, C);
+  RL_TS(attn, 6);
 
   // 4. y = x + o Wp^T + bp        (transformer.py:320, :405)
   {
     MmaTile<L, C> acc;
     acc.init();
-    WStream<C, C, B_NK>::run(acc, sq, LDC, sw, a.wp, C, nullptr, C);
+    AttnW<C>::Proj::template run<true>(acc, sq, LDC, sw, a.wp, C, nullptr, C);
+    RL_TS(attn, 7);
     const float* bp = a.bp;
     float* yw = a.y + woff;
     const bool resid = a.flags & RL_F_RESIDUAL;
@@ -101,11 +124,12 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_kernel(const rl_attn_
       yw[t * C + n] = v;
     });
   }
+  RL_TS(attn, 8);
 }
 
 // ---------------------------------------------------------------------------------------------
 template <int C>
-__host__ __device__ constexpr int attn_bwd_swf() { return WStream<C, C, B_KN>::FLOATS; }
+__host__ __device__ constexpr int attn_bwd_swf() { return cmax(AttnW<C>::Dgrad::FLOATS, AttnW<C>::DProj::FLOATS); }
 template <int C>
 size_t attn_bwd_smem(int L) {
   return sizeof(float) * (8 * (size_t)L * ld_mk(C) + 2 * ((size_t)L * C / 4) + attn_bwd_swf<C>() + 256 + 2 * C);
@@ -113,8 +137,6 @@ size_t attn_bwd_smem(int L) {
 
 template <int C, int WIN>
 __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_bwd_args a) {
-  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
-  pdl_trigger();   // let the next kernel get scheduled while this one runs
   extern __shared__ __align__(16) float smem[];
   constexpr int L = 2048 * WIN / C, H = C / RL_HD;
   constexpr int LDC = ld_mk(C), LC = L * C, LP = L * LDC;
@@ -134,6 +156,11 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   float* stabg = stab + 128;
   float* s_gb = stabg + 128;
   const int tid = threadIdx.x;
+  RL_TS(attn, 0);
+  AttnW<C>::DProj::prefetch(sw, a.wp, 1 << 30, nullptr, C);   // weights do not depend on the preceding kernels
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
+  RL_TS(attn, 1);
   const size_t woff = (size_t)blockIdx.x * LC;
   const float* gw = a.g + woff;
   const float* xw = a.x + woff;
@@ -151,15 +178,18 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   }
   for (int i = tid; i < 2 * C; i += RL_NT) s_gb[i] = 0.f;
   __syncthreads();
+  RL_TS(attn, 2);
 
   // 2. do = g Wp            (dgrad of proj; B(k,n) = Wp[k][n], natural layout)
   {
     MmaTile<L, C> acc;
     acc.init();
-    WStream<C, C, B_KN>::run(acc, sdq, LDC, sw, a.wp, 0, nullptr, C);
+    AttnW<C>::DProj::template run<true>(acc, sdq, LDC, sw, a.wp, 1 << 30, nullptr, C);
+    AttnW<C>::Dgrad::prefetch(sw, a.wq, C, a.wkv, C);         // lands while the attention core runs
     acc.epilogue([&](int t, int n, float v) { sdo[t * LDC + n] = v; });
   }
   __syncthreads();
+  RL_TS(attn, 3);
   // 3. D[h,i] = do_i . o_i
   for (int item = tid; item < H * L; item += RL_NT) {
     const int i = item % L, h = item / L;
@@ -169,16 +199,19 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   }
   __syncthreads();
 
-  constexpr bool FW = (C <= 16);   // narrow stages: weight gradients are accumulated in-CTA (no wgrad launch)
+  constexpr bool FW = (C <= RL_FW_MAXC);   // narrow stages: weight gradients are accumulated in-CTA (no wgrad launch)
   if (FW) cta_wgrad<C, C, L>(sdq, LDC, sdk, LDC, a.d_wp, a.d_bp);          // dWp = g^T o,  dbp = sum g
   if (FW) __syncthreads();
+  RL_TS(attn, 4);
 
   // 4. attention core backward on the tensor cores (attn_core.cuh): a query-major pass for dq (+ the R-wave table
   //    gradient) and a key-major pass for dk, dv; p is recomputed from the saved log-sum-exp.
   //    (sdk held o, last read in step 3 before a barrier)
   attn_core_bwd_dq<C, L>(sq, sk, sv, sdo, sD, sLse, sdq, stab, stabg, a.d_table != nullptr, W, c0);
+  RL_TS(attn, 5);
   attn_core_bwd_dkv<C, L>(sq, sk, sv, sdo, sD, sLse, sdk, sdv, stab, W, c0);
   __syncthreads();
+  RL_TS(attn, 6);
 
   // 5. dqkv scratch [t][dq | dk | dv] for the weight-gradient GEMMs
   if (!FW) {
@@ -191,19 +224,18 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
     }
   }
 
-  // 6. du = dq Wq + dk Wk + dv Wv       (K = 3C in three segments)
+  RL_TS(attn, 7);
+  // 6. du = [dq | dk | dv] [Wq ; Wk ; Wv]      (K = 3C: one weight stream over the three row blocks; sdq, sdk, sdv
+  //    are consecutive L x LDC arrays)
   {
     MmaTile<L, C> acc;
     acc.init();
-    for (int seg = 0; seg < 3; ++seg) {
-      const float* As = (seg == 0) ? sdq : (seg == 1) ? sdk : sdv;
-      const float* Wsrc = (seg == 0) ? a.wq : (seg == 1) ? a.wkv : a.wkv + (size_t)C * C;
-      WStream<C, C, B_KN>::run(acc, As, LDC, sw, Wsrc, 0, nullptr, C);
-    }
+    AttnW<C>::Dgrad::template run<true>(acc, sdq, LDC, sw, a.wq, C, a.wkv, C, C, LP);
     acc.epilogue([&](int t, int n, float v) { su[t * LDC + n] = v; });
   }
   __syncthreads();
 
+  RL_TS(attn, 8);
   // 7. LayerNorm backward, positional scale, residual
   float* dxw = a.dx + woff;
   float* uw = a.u + woff;
@@ -235,6 +267,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
     }
     __syncthreads();
   }
+  RL_TS(attn, 9);
   if (FW) {   // dWq = dq^T u, dWkv = [dk | dv]^T u  (u now sits in su)
     cta_wgrad<C, C, L>(sdq, LDC, su, LDC, a.d_wq, a.d_bq);
     cta_wgrad<C, C, L>(sdk, LDC, su, LDC, a.d_wkv, a.d_bkv);
@@ -242,6 +275,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   }
   if (a.d_table && W > 0)
     for (int i = tid; i < (2 * W - 1) * H; i += RL_NT) atomicAdd(a.d_table + i, stabg[i]);
+  RL_TS(attn, 10);
 }
 
 template <int C>
@@ -324,13 +358,13 @@ int rl_attn_bwd_main(const rl_attn_bwd_args* a, cudaStream_t st) {
 
 // true when the weight gradients of this shape are a separate launch (rl_attn_bwd_wgrad)
 bool rl_attn_bwd_has_wgrad(const rl_attn_bwd_args* a) {
-  return a->C > 16 && (a->d_wp || a->d_wq || a->d_wkv);
+  return a->C > RL_FW_MAXC && (a->d_wp || a->d_wq || a->d_wkv);
 }
 
 // weight gradients from (g, o) and the scratch tensors; may run on another stream once the main kernel is done
 int rl_attn_bwd_wgrad(const rl_attn_bwd_args* a, cudaStream_t st) {
   const int M = a->B * a->L, C = a->C;
-  if (C <= 16) return RL_OK;        // narrow stages accumulate their weight gradients inside the kernel
+  if (C <= RL_FW_MAXC) return RL_OK;        // narrow stages accumulate their weight gradients inside the kernel
   const RlWgradDesc d[3] = {{a->g, C, a->o, C, C, C, a->d_wp, a->d_bp},
                             {a->dqkv, 3 * C, a->u, C, C, C, a->d_wq, a->d_bq},
                             {a->dqkv + C, 3 * C, a->u, C, 2 * C, C, a->d_wkv, a->d_bkv}};

@@ -11,9 +11,26 @@
 #ifndef RL_MINB
 #define RL_MINB 1          // min CTAs per SM hint for __launch_bounds__
 #endif
+#ifndef RL_FW_MAXC
+#define RL_FW_MAXC 16      // stages with C <= this accumulate their weight gradients inside the data-gradient kernels
+#endif
 #define RL_HD 4            // head dim (model/transformer.py:277: dim // num_heads == 4 at every stage)
 #define RL_LOG2E 1.4426950408889634f
 #define RL_LN_EPS 1e-5f
+
+// phase timestamps (debug builds only, -DRL_TRACE): RL_TRACE_DEFINE(tag) once per translation unit, then
+// RL_TS(tag, i) stores the SM clock of thread 0 into slot i < 16 of this CTA; read with ralenet_debug_trace_read_<tag>
+#ifdef RL_TRACE
+#define RL_TRACE_DEFINE(tag)                                                          \
+  __device__ long long g_trace_##tag[4096 * 16];                                      \
+  extern "C" int ralenet_debug_trace_read_##tag(long long* out, int n) {              \
+    return (int)cudaMemcpyFromSymbol(out, g_trace_##tag, sizeof(long long) * n);      \
+  }
+#define RL_TS(tag, i) do { if (threadIdx.x == 0 && blockIdx.x < 4096) g_trace_##tag[blockIdx.x * 16 + (i)] = clock64(); } while (0)
+#else
+#define RL_TRACE_DEFINE(tag)
+#define RL_TS(tag, i) do { } while (0)
+#endif
 
 void rl_set_error(const char* fmt, ...);
 void rl_count_launch();
@@ -497,54 +514,76 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int STAGE_BUDGET = 6144;   // floats per pipeline stage (24 KB)
 
-template <int N, int K, int BL>
+// NS-stage ring of K chunks; BUDGET = floats per stage.  One __syncthreads per chunk: after the barrier of
+// iteration c every thread has finished the MMAs of chunk c-1, so its stage is refilled with chunk c+NS-1.
+// The first chunk can be issued long before the GEMM (prefetch(): before griddepcontrol.wait -- weights are never
+// written by a kernel that triggers its dependents early -- or right after the previous GEMM on the same staging
+// area), which hides the L2 latency of the weights behind the phase in between.
+template <int N, int K, int BL, int NS = 2, int BUDGET = STAGE_BUDGET, int KSEG = K>
 struct WStream {
-  static constexpr int KC = (BL == B_NK) ? kc_nk(N, K, STAGE_BUDGET) : kc_kn(N, K, STAGE_BUDGET);
+  // KSEG: a chunk never straddles a multiple of KSEG (K = several concatenated operands of KSEG columns each)
+  static constexpr int KC = (BL == B_NK) ? kc_nk(N, KSEG, BUDGET) : kc_kn(N, KSEG, BUDGET);
   static constexpr int LD = (BL == B_NK) ? KC + 4 : ld_kn(N);
   static constexpr int STAGE = (BL == B_NK) ? N * LD : KC * LD;     // floats per stage
-  static constexpr int FLOATS = 2 * STAGE;
   static constexpr int NCHUNK = K / KC;
-  static_assert(K % KC == 0 && KC % 8 == 0, "WStream: chunking");
+  static constexpr int NSE = (NS < NCHUNK) ? NS : (NCHUNK < 2 ? 1 : NCHUNK);   // stages actually used
+  static constexpr int FLOATS = NSE * STAGE;
+  static_assert(K % KC == 0 && KC % 8 == 0 && NS >= 2, "WStream: chunking");
 
-  // B_NK: W(n, k) = (n < n_split ? W0[n*ldw + k] : W1[(n-n_split)*ldw + k])     (y = x W^T, W = [N][K])
-  // B_KN: W(k, n) = W0[k*ldw + n]                                                (dx = dy W,  W = [K][N])
-  __device__ static __forceinline__ void issue(float* dst, const float* __restrict__ W0, int n_split,
+  // B_NK: W(n, k) = (n < split ? W0[n*ldw + k] : W1[(n-split)*ldw + k])         (y = x W^T, W = [N][K])
+  // B_KN: W(k, n) = (k < split ? W0[k*ldw + n] : W1[(k-split)*ldw + n])         (dx = dy W,  W = [K][N])
+  __device__ static __forceinline__ void issue(float* dst, const float* __restrict__ W0, int split,
                                                const float* __restrict__ W1, int ldw, int k0) {
     if (BL == B_NK) {
       constexpr int V = KC / 4;
       for (int i = threadIdx.x; i < N * V; i += RL_NT) {
         const int n = i / V, c = (i % V) * 4;
-        const float* row = (n < n_split) ? W0 + (size_t)n * ldw : W1 + (size_t)(n - n_split) * ldw;
+        const float* row = (n < split) ? W0 + (size_t)n * ldw : W1 + (size_t)(n - split) * ldw;
         cp_async16(dst + n * LD + c, row + k0 + c);
       }
     } else {
       constexpr int V = N / 4;
       for (int i = threadIdx.x; i < KC * V; i += RL_NT) {
-        const int r = i / V, c = (i % V) * 4;
-        cp_async16(dst + r * LD + c, W0 + (size_t)(k0 + r) * ldw + c);
+        const int r = i / V, c = (i % V) * 4, k = k0 + r;
+        const float* row = (k < split) ? W0 + (size_t)k * ldw : W1 + (size_t)(k - split) * ldw;
+        cp_async16(dst + r * LD + c, row + c);
       }
     }
     cp_async_commit();
   }
 
-  // acc += A[:, 0:K] * W      (A in smem, A_MK with stride lda; sw holds FLOATS floats)
-  template <class Acc>
+  // issue chunk 0 into stage 0; the staging area must be free (a barrier since its last reader) and no other
+  // cp.async group may be committed between this call and the matching run<true>()
+  __device__ static __forceinline__ void prefetch(float* sw, const float* __restrict__ W0, int split,
+                                                  const float* __restrict__ W1, int ldw) {
+    issue(sw, W0, split, W1, ldw, 0);
+  }
+
+  // acc += A[:, 0:K] * W      (A in smem, A_MK with stride lda; sw holds FLOATS floats).  When the K range is the
+  // concatenation of several A arrays (a_seg columns each, a_seg % KC == 0) the next one starts a_seg_stride floats
+  // after the previous.  Ends with a barrier: afterwards sw (and A) may be overwritten.
+  template <bool PREFETCHED = false, class Acc>
   __device__ static __forceinline__ void run(Acc& acc, const float* A, int lda, float* sw,
-                                             const float* __restrict__ W0, int n_split,
-                                             const float* __restrict__ W1, int ldw) {
-    issue(sw, W0, n_split, W1, ldw, 0);
+                                             const float* __restrict__ W0, int split,
+                                             const float* __restrict__ W1, int ldw, int a_seg = K,
+                                             int a_seg_stride = 0) {
+    if (!PREFETCHED) issue(sw, W0, split, W1, ldw, 0);
+#pragma unroll
+    for (int s = 1; s < NSE - 1; ++s) issue(sw + s * STAGE, W0, split, W1, ldw, s * KC);
 #pragma unroll 1
     for (int c = 0; c < NCHUNK; ++c) {
-      if (c + 1 < NCHUNK) {
-        issue(sw + ((c + 1) & 1) * STAGE, W0, n_split, W1, ldw, (c + 1) * KC);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
+      cp_async_wait<(NSE >= 2) ? NSE - 2 : 0>();     // chunk c has landed (NSE-2 younger groups may be in flight)
+      __syncthreads();
+      if (NSE >= 2) {
+        if (c + NSE - 1 < NCHUNK)
+          issue(sw + ((c + NSE - 1) % NSE) * STAGE, W0, split, W1, ldw, (c + NSE - 1) * KC);
+        else
+          cp_async_commit();                          // empty group keeps the wait count static
       }
-      __syncthreads();
-      acc.template mac<A_MK, BL>(A + c * KC, lda, sw + (c & 1) * STAGE, LD, KC);
-      __syncthreads();
+      const int k0 = c * KC;
+      acc.template mac<A_MK, BL>(A + (k0 / a_seg) * a_seg_stride + (k0 % a_seg), lda, sw + (c % NSE) * STAGE, LD, KC);
     }
+    __syncthreads();
   }
 };
 

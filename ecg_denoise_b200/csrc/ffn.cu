@@ -30,8 +30,6 @@ size_t ffn_fwd_smem(int L) {
 
 template <int C, int WIN>
 __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_kernel(const rl_ffn_fwd_args a) {
-  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
-  pdl_trigger();   // let the next kernel get scheduled while this one runs
   extern __shared__ __align__(16) float smem[];
   constexpr int L = 2048 * WIN / C;
   constexpr int LDC = ld_mk(C);
@@ -40,6 +38,10 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_kernel(const rl_ffn_fw
   float* sh = su + L * LDC;
   float* sw = sh + L * LDH;
   float* sfir = sw + ffn_fwd_swf<C>();
+  // the weights are not produced by the preceding kernels of the step: start pulling them before the dependency wait
+  WStream<HC, C, B_NK>::prefetch(sw, a.w1, HC, nullptr, C);
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   const int tid = threadIdx.x;
   const size_t woff = (size_t)blockIdx.x * L * C;
   const float* xw = a.x + woff;
@@ -60,7 +62,8 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_kernel(const rl_ffn_fw
   {
     MmaTile<L, HC> acc;
     acc.init();
-    WStream<HC, C, B_NK>::run(acc, su, LDC, sw, a.w1, HC, nullptr, C);
+    WStream<HC, C, B_NK>::template run<true>(acc, su, LDC, sw, a.w1, HC, nullptr, C);
+    WStream<C, HC, B_NK>::prefetch(sw, a.w2, C, nullptr, HC);      // lands behind the GELU / local-enhancement phase
     const float* b1 = a.b1;
     float* hs = a.h ? a.h + (size_t)blockIdx.x * L * HC : nullptr;
     acc.epilogue([&](int t, int n, float v) {
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_kernel(const rl_ffn_fw
   {
     MmaTile<L, C> acc;
     acc.init();
-    WStream<C, HC, B_NK>::run(acc, sh, LDH, sw, a.w2, C, nullptr, HC);
+    WStream<C, HC, B_NK>::template run<true>(acc, sh, LDH, sw, a.w2, C, nullptr, HC);
     const float* b2 = a.b2;
     const float* ex = a.extra ? a.extra + woff : nullptr;
     float* yw = a.y + woff;
@@ -129,14 +132,12 @@ __host__ __device__ constexpr int ffn_bwd_swf() {
 template <int C>
 size_t ffn_bwd_smem(int L, bool dw) {
   // narrow stages (C <= 16) keep g2 in shared memory as well for the in-CTA weight gradients
-  return sizeof(float) * (2 * (size_t)L * ld_mk(C) + ((dw ? 2 : 1) + (C <= 16 ? 1 : 0)) * (size_t)L * ld_mk(4 * C) +
+  return sizeof(float) * (2 * (size_t)L * ld_mk(C) + ((dw ? 2 : 1) + (C <= RL_FW_MAXC ? 1 : 0)) * (size_t)L * ld_mk(4 * C) +
                           ffn_bwd_swf<C>() + 3 * (size_t)L + 2 * C + 64);
 }
 
 template <int C, int WIN, bool DW>
 __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bwd_args a) {
-  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
-  pdl_trigger();   // let the next kernel get scheduled while this one runs
   extern __shared__ __align__(16) float smem[];
   constexpr int L = 2048 * WIN / C;
   constexpr int LDC = ld_mk(C);
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
   float* su = sg + L * LDC;               // du (LN2 output gradient)
   float* sd = su + L * LDC;               // df / dh
   float* sh = sd + L * LDH;               // g1 = GELU(h), depthwise mode only
-  constexpr bool FW = (C <= 16);          // narrow stages: weight gradients accumulated in-CTA (no wgrad launch)
+  constexpr bool FW = (C <= RL_FW_MAXC);          // narrow stages: weight gradients accumulated in-CTA (no wgrad launch)
   float* sg2 = sh + (DW ? L * LDH : 0);   // g2, narrow stages only
   float* sw = sg2 + (FW ? L * LDH : 0);
   float* sg10 = sw + ffn_bwd_swf<C>();    // g1[:,0]
@@ -154,6 +155,9 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
   float* s_gb = sdf0 + L;
   float* s_red = s_gb + 2 * C;
   const int tid = threadIdx.x;
+  WStream<HC, C, B_KN>::prefetch(sw, a.w2, 1 << 30, nullptr, HC);   // weights do not depend on the preceding kernels
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   const size_t woff = (size_t)blockIdx.x * L * C;
   const size_t hoff = (size_t)blockIdx.x * L * HC;
   const float* gw = a.g + woff;
@@ -195,7 +199,8 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
   {
     MmaTile<L, HC> acc;
     acc.init();
-    WStream<HC, C, B_KN>::run(acc, sg, LDC, sw, a.w2, 0, nullptr, HC);
+    WStream<HC, C, B_KN>::template run<true>(acc, sg, LDC, sw, a.w2, 1 << 30, nullptr, HC);
+    WStream<C, HC, B_KN>::prefetch(sw, a.w1, 1 << 30, nullptr, C);    // lands behind the GELU' / FIR-adjoint phase
     acc.epilogue([&](int t, int n, float v) {
       if (DW) {
         const float g1 = sh[t * LDH + n];
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
   {
     MmaTile<L, C> acc;
     acc.init();
-    WStream<C, HC, B_KN>::run(acc, sd, LDH, sw, a.w1, 0, nullptr, C);
+    WStream<C, HC, B_KN>::template run<true>(acc, sd, LDH, sw, a.w1, 1 << 30, nullptr, C);
     acc.epilogue([&](int t, int n, float v) { su[t * LDC + n] = v; });
   }
   __syncthreads();
@@ -405,12 +410,12 @@ int rl_ffn_bwd_main(const rl_ffn_bwd_args* a, cudaStream_t st) {
   return rc;
 }
 
-bool rl_ffn_bwd_has_wgrad(const rl_ffn_bwd_args* a) { return a->C > 16 && (a->d_w1 || a->d_w2); }
+bool rl_ffn_bwd_has_wgrad(const rl_ffn_bwd_args* a) { return a->C > RL_FW_MAXC && (a->d_w1 || a->d_w2); }
 
 // weight gradients from (g, g2) and (dh, u); may run on another stream once the main kernel is done
 int rl_ffn_bwd_wgrad(const rl_ffn_bwd_args* a, cudaStream_t st) {
   const int M = a->B * a->L, C = a->C;
-  if (C <= 16) return RL_OK;        // narrow stages accumulate their weight gradients inside the kernel
+  if (C <= RL_FW_MAXC) return RL_OK;        // narrow stages accumulate their weight gradients inside the kernel
   const RlWgradDesc d[2] = {{a->g, C, a->g2, 4 * C, C, 4 * C, a->d_w2, a->d_b2},
                             {a->dh, 4 * C, a->u, C, 4 * C, C, a->d_w1, a->d_b1}};
   return rl_launch_wgrad_group(d, 2, M, st);

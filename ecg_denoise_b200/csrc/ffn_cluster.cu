@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_cluster_kernel(const r
   {
     MmaTile<TM, TH> acc;
     acc.init();
-    WStream<TH, C, B_KN>::run(acc, sg, LDC, sw, a.w2 + (size_t)r * TH, 0, nullptr, HC);
+    WStream<TH, C, B_KN>::run(acc, sg, LDC, sw, a.w2 + (size_t)r * TH, 1 << 30, nullptr, HC);
     acc.epilogue([&](int t, int n, float v) {
       const bool ok = t < nvalid;
       float g1, d1;
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_cluster_kernel(const r
   {
     MmaTile<TM, C> acc;
     acc.init();
-    WStream<C, TH, B_KN>::run(acc, sd, LDT, sw, a.w1 + (size_t)r * TH * C, 0, nullptr, C);
+    WStream<C, TH, B_KN>::run(acc, sd, LDT, sw, a.w1 + (size_t)r * TH * C, 1 << 30, nullptr, C);
     acc.epilogue([&](int t, int n, float v) { sp[t * LDC + n] = v; });
   }
 

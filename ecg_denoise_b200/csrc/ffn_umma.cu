@@ -21,16 +21,7 @@
 
 namespace cg = cooperative_groups;
 
-// phase timestamps of the forward kernel (debug builds only: -DRL_TRACE): [cta][16] SM clock values
-#ifdef RL_TRACE
-__device__ long long g_trace[1024 * 16];
-#define RL_TS(i) do { if (threadIdx.x == 0) g_trace[blockIdx.x * 16 + (i)] = clock64(); } while (0)
-extern "C" int ralenet_debug_trace_read(long long* out, int n) {
-  return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * n);
-}
-#else
-#define RL_TS(i) do { } while (0)
-#endif
+RL_TRACE_DEFINE(umma)
 
 namespace {
 
@@ -73,10 +64,10 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
 #pragma unroll
     for (int j = 0; j < C / KC; ++j) w1r[j].load(w1s + j * KC, C, TS);
   }
-  RL_TS(0);
+  RL_TS(umma, 0);
   pdl_wait();
   pdl_trigger();
-  RL_TS(1);
+  RL_TS(umma, 1);
   extern __shared__ __align__(128) float smem[];
   float* sA_hi = smem;
   float* sA_lo = sA_hi + FwdSmem<C>::A_FLOATS;
@@ -100,7 +91,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
     umma::fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc<TMEM_COLS>(tmem_slot);
-  RL_TS(2);
+  RL_TS(umma, 2);
 
   // 1. LN2 over the TM tokens -> A tile (K-major, KT = C) with its tf32 remainder.  A warp owns 8 rows; lane =
   //    (row % 8, 16-byte chunk % 4), so global reads cover full sectors and the tile stores are contiguous.
@@ -156,7 +147,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
   umma::tc_fence_after();
   const uint32_t tb = *tmem_slot;
   Ring ring{bars, 0};
-  RL_TS(3);
+  RL_TS(umma, 3);
 
   // 2. hidden slice: h = u W1[128 r : 128 r + 128]^T   (M = TM, N = TS, K = C) -> TMEM columns [0, TS)
   {
@@ -184,10 +175,10 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
 #pragma unroll
     for (int j = 0; j < TS / KC; ++j) w2r[j].load(w2s + j * KC, HC, C);
   }
-  RL_TS(4);
+  RL_TS(umma, 4);
   ring.wait_last();
   umma::tc_fence_after();
-  RL_TS(5);
+  RL_TS(umma, 5);
 
   // 3. epilogue 1: + b1, save h, GELU, local enhancement (3-tap FIR along the tokens of each window on hidden
   //    channel 0 = column 0 of slice 0), second GELU -> g2 tile (K-major, KT = TS) with remainder, over the dead u tile.
@@ -249,7 +240,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
     }
   }
   umma::tc_fence_before();     // the tcgen05.ld reads of the fc1 accumulator precede the barrier below
-  RL_TS(6);
+  RL_TS(umma, 6);
 
   // 4. partial output of this hidden slice: yp = g2 W2[:, 128 r : 128 r + 128]^T  (M = TM, N = C, K = TS)
   //    -> TMEM columns [TS, TS + C)
@@ -273,7 +264,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
   }
   ring.wait_last();
   umma::tc_fence_after();
-  RL_TS(7);
+  RL_TS(umma, 7);
 
   // 5. epilogue 2: partial tile -> shared memory [TM][C + 4] (over the dead g2 tile), DSMEM reduction:
   //    CTA r finishes rows [r * TM / NSL, (r + 1) * TM / NSL)
@@ -293,9 +284,9 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
     }
   }
   umma::tc_fence_before();
-  RL_TS(8);
+  RL_TS(umma, 8);
   cluster.sync();
-  RL_TS(9);
+  RL_TS(umma, 9);
   {
     constexpr int RPC = TM / NSL;                             // rows finished by this CTA
     const float* part[NSL];
@@ -329,10 +320,10 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
       *reinterpret_cast<float4*>(a.y + g) = s;
     }
   }
-  RL_TS(10);
+  RL_TS(umma, 10);
   cluster.sync();     // nobody may exit while its partial tile is still being read
   if (warp == 0) umma::tmem_dealloc<TMEM_COLS>(tb);
-  RL_TS(11);
+  RL_TS(umma, 11);
 }
 
 // ---------------------------------------------------------------------------------------------

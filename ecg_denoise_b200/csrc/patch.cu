@@ -26,14 +26,15 @@ size_t patch_smem(int rows) { return sizeof(float) * (2 * (size_t)rows * ld_mk(C
 
 template <int CN, int WIN>
 __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_fwd_kernel(const rl_patch_fwd_args a) {
-  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
-  pdl_trigger();   // let the next kernel get scheduled while this one runs
   extern __shared__ __align__(16) float smem[];
   constexpr int LDA = ld_mk(CN);
   constexpr int rows = 2048 * WIN / CN;
   const int L = a.L, C = a.C, mode = a.mode;
   float* su = smem;
   float* sw = su + 2 * rows * LDA;
+  WStream<CN, CN, B_NK>::prefetch(sw, a.w, CN, nullptr, CN);   // weights do not depend on the preceding kernels
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   const size_t woff = (size_t)blockIdx.x * L * C;
   const float* xw = a.x + woff;
   {
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_fwd_kernel(const rl_patc
   __syncthreads();
   MmaTile<rows, CN> acc;
   acc.init();
-  WStream<CN, CN, B_NK>::run(acc, su, LDA, sw, a.w, CN, nullptr, CN);
+  WStream<CN, CN, B_NK>::template run<true>(acc, su, LDA, sw, a.w, CN, nullptr, CN);
   const float* sk = a.skip ? a.skip + woff : nullptr;
   float* yw = a.y + woff;
   acc.epilogue([&](int r, int n, float v) {
@@ -62,8 +63,6 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_fwd_kernel(const rl_patc
 
 template <int CN, int WIN>
 __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_bwd_kernel(const rl_patch_bwd_args a, float* __restrict__ gsum) {
-  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
-  pdl_trigger();   // let the next kernel get scheduled while this one runs
   extern __shared__ __align__(16) float smem[];
   constexpr int LDA = ld_mk(CN);
   constexpr int rows = 2048 * WIN / CN;
@@ -71,6 +70,9 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_bwd_kernel(const rl_patc
   float* sg = smem;
   float* su = sg + rows * LDA;
   float* sw = su + rows * LDA;
+  WStream<CN, CN, B_KN>::prefetch(sw, a.w, 1 << 30, nullptr, CN);   // weights do not depend on the preceding kernels
+  pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+  pdl_trigger();   // let the next kernel get scheduled while this one runs
   float* s_gb = sw + patch_swf<CN>();
   const int tid = threadIdx.x;
   const size_t woff = (size_t)blockIdx.x * L * C;
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_bwd_kernel(const rl_patc
   {
     MmaTile<rows, CN> acc;
     acc.init();
-    WStream<CN, CN, B_KN>::run(acc, sg, LDA, sw, a.w, 0, nullptr, CN);
+    WStream<CN, CN, B_KN>::template run<true>(acc, sg, LDA, sw, a.w, 1 << 30, nullptr, CN);
     acc.epilogue([&](int r, int n, float v) { su[r * LDA + n] = v; });
   }
   __syncthreads();

@@ -5,7 +5,7 @@
 tag=${1:-step}
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 3 --warmup 3 --graph off --no-cpu-baseline --no-profile"
-RX='regex:(attn_bwd_kernel<16|attn_bwd_kernel<8|attn_fwd_kernel<16|attn_fwd_kernel<128|ffn_bwd_kernel<16|ffn_fwd_umma_kernel<128|ffn_bwd_umma_kernel<128|wgrad_group_kernel<64, 32|patch_bwd_kernel<32)'
+RX='regex:(attn_bwd_kernel<.int.16,|attn_bwd_kernel<.int.8,|attn_fwd_kernel<.int.16,|attn_fwd_kernel<.int.128,|ffn_bwd_kernel<.int.16,|ffn_fwd_umma_kernel<.int.128|ffn_bwd_umma_kernel<.int.128|wgrad_group_kernel<.int.64|patch_bwd_kernel<.int.32,)'
 timeout 420 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k "$RX" -s 60 -c 14 \
   -o gpurun_out/${tag}_top $BENCH > gpurun_out/${tag}_ncu.log 2>&1
 ncu -i gpurun_out/${tag}_top.ncu-rep --page raw --csv > gpurun_out/${tag}_top_raw.csv 2>/dev/null

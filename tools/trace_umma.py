@@ -34,8 +34,8 @@ e1.record(); torch.cuda.synchronize()
 print("avg kernel+launch us (back to back):", 1e3 * e0.elapsed_time(e1) / 20)
 ncta = (B * L // 128) * (4 * C // 128)
 buf = (ctypes.c_longlong * (ncta * 16))()
-lib.ralenet_debug_trace_read.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
-print("read rc", lib.ralenet_debug_trace_read(buf, ncta * 16))
+lib.ralenet_debug_trace_read_umma.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
+print("read rc", lib.ralenet_debug_trace_read_umma(buf, ncta * 16))
 t = np.array(buf[:], dtype=np.int64).reshape(ncta, 16)[:, :12]
 d = np.diff(t, axis=1)
 names = ["prefetch->pdl", "pdl->alloc/init", "LN tile", "fc1 stage+issue", "wait fc1", "epilogue1", "fc2 stage+issue+wait",

@@ -47,7 +47,8 @@ def algorithmic_work(label: str, B: int, L0: int = 256):
     name, _, tag = label.partition("<")
     tags = [int(t) for t in tag.rstrip(">").split(",")] if tag else []
     N = 8 * L0                       # floats per window per activation tensor
-    name = {"ffn_fwd_cluster": "ffn_fwd_kernel", "ffn_bwd_cluster": "ffn_bwd_kernel"}.get(name, name)
+    name = {"ffn_fwd_cluster": "ffn_fwd_kernel", "ffn_bwd_cluster": "ffn_bwd_kernel",
+            "ffn_fwd_umma": "ffn_fwd_kernel", "ffn_bwd_umma": "ffn_bwd_kernel"}.get(name, name)
     if name in ("attn_fwd_kernel", "attn_bwd_kernel", "ffn_fwd_kernel", "ffn_bwd_kernel"):
         C = tags[0]
         L = N // C

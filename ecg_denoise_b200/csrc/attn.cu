@@ -20,42 +20,49 @@ namespace {
 
 // weight streams: the wide stages pull their weights through deeper rings of smaller chunks (more loads in flight;
 // a 2-stage ring leaves the L2 latency of every chunk exposed), sized so that two CTAs still fit on an SM
-template <int C>
+template <int C, int NS = ((C >= 64) ? 4 : 2)>
 struct AttnW {
-  static constexpr int NS = (C >= 64) ? 4 : 2;
   using Qkv = WStream<3 * C, C, B_NK, NS, STAGE_BUDGET>;
   using Proj = WStream<C, C, B_NK, NS, (C >= 128) ? STAGE_BUDGET / 2 : STAGE_BUDGET>;
   using Dgrad = WStream<C, 3 * C, B_KN, NS, (C >= 64) ? STAGE_BUDGET / 2 : STAGE_BUDGET, C>;   // du = [dq|dk|dv] [Wq;Wkv]
   using DProj = WStream<C, C, B_KN, NS, (C >= 64) ? STAGE_BUDGET / 2 : STAGE_BUDGET>;          // do = g Wp
 };
-template <int C>
+// forward: NWC windows per CTA.  At the wide stages a window has only 32 / 16 tokens while its CTA streams 64 / 256 KB
+// of weights, and the kernel is bound by that L2 -> SM traffic (profiles/r1_v7_trace_attn.txt); two consecutive
+// windows per CTA (M = 2L rows) halve it.  The 2-window variant keeps a 2-stage ring so that two CTAs still fit an SM.
+template <int C, int NWC>
+using AttnWF = AttnW<C, (NWC == 2) ? 2 : ((C >= 64) ? 4 : 2)>;
+template <int C, int NWC>
 __host__ __device__ constexpr int attn_fwd_swf() {
-  return cmax(AttnW<C>::Qkv::FLOATS, AttnW<C>::Proj::FLOATS);
+  return cmax(AttnWF<C, NWC>::Qkv::FLOATS, AttnWF<C, NWC>::Proj::FLOATS);
 }
-template <int C>
-size_t attn_fwd_smem(int L) { return sizeof(float) * (4 * (size_t)L * ld_mk(C) + attn_fwd_swf<C>() + 128); }
+template <int C, int NWC>
+size_t attn_fwd_smem(int L) {
+  return sizeof(float) * (4 * (size_t)NWC * L * ld_mk(C) + attn_fwd_swf<C, NWC>() + 128);
+}
 
 // ---------------------------------------------------------------------------------------------
-template <int C, int WIN>
-__global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_kernel(const rl_attn_fwd_args a) {
+template <int C, int WIN, int NWC>
+__global__ void __launch_bounds__(RL_NT, (NWC >= 4) ? 1 : RL_MINB) attn_fwd_kernel(const rl_attn_fwd_args a) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int L = 2048 * WIN / C, H = C / RL_HD;
+  constexpr int L = 2048 * WIN / C, H = C / RL_HD, M = NWC * L;      // M token rows (NWC whole windows) per CTA
   constexpr int LDC = ld_mk(C);
+  using WS = AttnWF<C, NWC>;
   const int W = a.W, c0 = a.c0;
   float* su = smem;
-  float* sq = su + L * LDC;
-  float* sk = sq + L * LDC;
-  float* sv = sk + L * LDC;
-  float* sw = sv + L * LDC;
-  float* stab = sw + attn_fwd_swf<C>();
+  float* sq = su + M * LDC;
+  float* sk = sq + M * LDC;
+  float* sv = sk + M * LDC;
+  float* sw = sv + M * LDC;
+  float* stab = sw + attn_fwd_swf<C, NWC>();
   // the weights are not produced by the preceding kernels of the step: start pulling them before the dependency wait
   RL_TS(attn, 0);
-  AttnW<C>::Qkv::prefetch(sw, a.wq, C, a.wkv, C);
+  WS::Qkv::prefetch(sw, a.wq, C, a.wkv, C);
   pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
   pdl_trigger();   // let the next kernel get scheduled while this one runs
   RL_TS(attn, 1);
   const int tid = threadIdx.x;
-  const size_t woff = (size_t)blockIdx.x * L * C;
+  const size_t woff = (size_t)blockIdx.x * M * C;
   const float* xw = a.x + woff;
 
   // 1. x*sqrt(C) + P -> LayerNorm -> su          (transformer.py:386-387)
@@ -65,10 +72,10 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_kernel(const rl_attn_
     const float* lw = a.ln_w;
     const float* lb = a.ln_b;
     ln_forward_rows<C>(
-        L, [&](int t, int c) { return fmaf(__ldg(xw + t * C + c), sc, __ldg(pe + t * C + c)); },
+        M, [&](int t, int c) { return fmaf(__ldg(xw + t * C + c), sc, __ldg(pe + (t % L) * C + c)); },
         [&](int t, int c, float zh) { su[t * LDC + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c)); });
   } else {
-    copy_rows_g2s(su, LDC, xw, L, C);
+    copy_rows_g2s(su, LDC, xw, M, C);
   }
   if (W > 0)
     for (int i = tid; i < (2 * W - 1) * H; i += RL_NT) stab[i] = __ldg(a.table + i) * RL_LOG2E;
@@ -77,10 +84,10 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_kernel(const rl_attn_
 
   // 2. [q|k|v] = u [Wq;Wkv]^T + b   (N = 3C, K = C): tensor-core GEMM, weights streamed through sw in K chunks
   {
-    MmaTile<L, 3 * C> acc;
+    MmaTile<M, 3 * C> acc;
     acc.init();
-    AttnW<C>::Qkv::template run<true>(acc, su, LDC, sw, a.wq, C, a.wkv, C);
-    AttnW<C>::Proj::prefetch(sw, a.wp, C, nullptr, C);        // lands while the attention core runs
+    WS::Qkv::template run<true>(acc, su, LDC, sw, a.wq, C, a.wkv, C);
+    WS::Proj::prefetch(sw, a.wp, C, nullptr, C);              // lands while the attention core runs
     const float* bq = a.bq;
     const float* bkv = a.bkv;
     acc.epilogue([&](int t, int n, float v) {
@@ -95,25 +102,28 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_kernel(const rl_attn_
   __syncthreads();
   RL_TS(attn, 3);
   if (a.q) {
-    copy_rows_s2g(a.q + woff, sq, LDC, L, C);
-    copy_rows_s2g(a.k + woff, sk, LDC, L, C);
-    copy_rows_s2g(a.v + woff, sv, LDC, L, C);
+    copy_rows_s2g(a.q + woff, sq, LDC, M, C);
+    copy_rows_s2g(a.k + woff, sk, LDC, M, C);
+    copy_rows_s2g(a.v + woff, sv, LDC, M, C);
   }
   RL_TS(attn, 4);
 
   // 3. attention core on the tensor cores (attn_core.cuh): one (head, 16-query tile) per warp, online softmax in
-  //    the log2 domain; o overwrites q in place.
-  attn_core_fwd<C, L>(sq, sk, sv, stab, W, c0, a.lse ? a.lse + (size_t)blockIdx.x * H * L : nullptr);
+  //    the log2 domain; o overwrites q in place.  Windows attend only within themselves.
+#pragma unroll
+  for (int w = 0; w < NWC; ++w)
+    attn_core_fwd<C, L>(sq + w * L * LDC, sk + w * L * LDC, sv + w * L * LDC, stab, W, c0,
+                        a.lse ? a.lse + ((size_t)blockIdx.x * NWC + w) * H * L : nullptr);
   __syncthreads();
   RL_TS(attn, 5);
-  if (a.o) copy_rows_s2g(a.o + woff, sq, LDC, L, C);
+  if (a.o) copy_rows_s2g(a.o + woff, sq, LDC, M, C);
   RL_TS(attn, 6);
 
   // 4. y = x + o Wp^T + bp        (transformer.py:320, :405)
   {
-    MmaTile<L, C> acc;
+    MmaTile<M, C> acc;
     acc.init();
-    AttnW<C>::Proj::template run<true>(acc, sq, LDC, sw, a.wp, C, nullptr, C);
+    WS::Proj::template run<true>(acc, sq, LDC, sw, a.wp, C, nullptr, C);
     RL_TS(attn, 7);
     const float* bp = a.bp;
     float* yw = a.y + woff;
@@ -278,18 +288,50 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   RL_TS(attn, 10);
 }
 
+#ifndef RL_NWC_MIN_B
+#define RL_NWC_MIN_B 512      // batches at least this large put two windows on a CTA at the wide stages (at the
+#endif                        // benchmark batch of 256 the halved CTA count costs more than the weight traffic saves)
+// (four windows per CTA at C = 128 -- one 170 KB CTA per SM -- measured slower than two: 320 vs 294 us at B = 4096)
+
+// `a` advanced by w0 windows, n windows long
+rl_attn_fwd_args attn_fwd_slice(const rl_attn_fwd_args& a, int w0, int n) {
+  rl_attn_fwd_args s = a;
+  const size_t off = (size_t)w0 * a.L * a.C;
+  s.B = n;
+  s.x = a.x + off;
+  s.y = a.y + off;
+  if (a.q) { s.q = a.q + off; s.k = a.k + off; s.v = a.v + off; s.o = a.o + off; }
+  if (a.lse) s.lse = a.lse + (size_t)w0 * a.H * a.L;
+  return s;
+}
+
+// launches floor(B / NWC) CTAs of NWC windows each; returns the number of windows covered through *done
+template <int C, int NWC>
+int launch_fwd_groups(const rl_attn_fwd_args* a, cudaStream_t st, int* done) {
+  const size_t smem = attn_fwd_smem<C, NWC>(a->L);
+  if (int rc = rl_set_smem(attn_fwd_kernel<C, 1, NWC>, smem)) return rc;
+  rl_launch_pdl(attn_fwd_kernel<C, 1, NWC>, dim3(a->B / NWC), dim3(RL_NT), smem, st, *a);
+  *done = (a->B / NWC) * NWC;
+  return rl_check_launch("attn_fwd_kernel", C, NWC);
+}
+
 template <int C>
 int launch_fwd(const rl_attn_fwd_args* a, cudaStream_t st) {
   const int win = a->L * C / 2048;
-  const size_t smem = attn_fwd_smem<C>(a->L);
-  if (win == 1) {
-    if (int rc = rl_set_smem(attn_fwd_kernel<C, 1>, smem)) return rc;
-    rl_launch_pdl(attn_fwd_kernel<C, 1>, dim3(a->B), dim3(RL_NT), smem, st, *a);
-  } else {
-    if (int rc = rl_set_smem(attn_fwd_kernel<C, 2>, smem)) return rc;
-    rl_launch_pdl(attn_fwd_kernel<C, 2>, dim3(a->B), dim3(RL_NT), smem, st, *a);
+  if (win != 1) {
+    const size_t smem = attn_fwd_smem<C, 1>(a->L);
+    if (int rc = rl_set_smem(attn_fwd_kernel<C, 2, 1>, smem)) return rc;
+    rl_launch_pdl(attn_fwd_kernel<C, 2, 1>, dim3(a->B), dim3(RL_NT), smem, st, *a);
+    return rl_check_launch("attn_fwd_kernel", C);
   }
-  return rl_check_launch("attn_fwd_kernel", C);
+  int done = 0;
+  if (C >= 64 && a->B >= RL_NWC_MIN_B) {
+    if (int rc = launch_fwd_groups<C, (C >= 64) ? 2 : 1>(a, st, &done)) return rc;
+  }
+  if (done == a->B) return RL_OK;
+  const rl_attn_fwd_args rest = attn_fwd_slice(*a, done, a->B - done);     // the odd windows, one per CTA
+  int d1 = 0;
+  return launch_fwd_groups<C, 1>(&rest, st, &d1);
 }
 
 template <int C>

@@ -102,6 +102,46 @@ def test_attn_block(ops, stage, bias):
         _cmp(tag + "/d_table", tt.grad, gr["table"])
 
 
+@pytest.mark.parametrize("stage", [3, 4])
+def test_attn_fwd_paired_windows_bit_identical(ops, stage):
+    """At the wide stages large batches put two windows on a CTA (attn.cu, NWC) and the odd last windows go
+    through the one-window kernel: outputs and every saved tensor must equal, bit for bit, what the one-window
+    kernel gives on the same windows in small batches (no window may see its CTA neighbour)."""
+    rs = np.random.RandomState(300 + stage)
+    C, H, L = O.CHANNELS[stage], O.HEADS[stage], O.LENGTHS[stage]
+    B = 515                                # 257 two-window CTAs + one odd window
+    p = _block_params(rs, C, 0)
+    W = O.RW_WINDOW[stage] if stage < 4 else 0
+    table = (0.5 * _rand(rs, 2 * W - 1, H)).float().cuda() if W else None
+    x = _rand(rs, B, L, C).float().cuda()
+    d = {k: v.float().cuda() for k, v in p.items()}
+
+    def run(xs):
+        with torch.no_grad():
+            return ops.AttnBlockFn.apply(xs, d["norm1.weight"], d["norm1.bias"], d["attn.qkv_proj.to_q.weight"],
+                                         d["attn.qkv_proj.to_q.bias"], d["attn.qkv_proj.to_kv.weight"],
+                                         d["attn.qkv_proj.to_kv.bias"], d["attn.proj.weight"], d["attn.proj.bias"],
+                                         table, H, W, (L - W) // 2 if W else 0, ops.RL_F_PRENORM | ops.RL_F_RESIDUAL)
+
+    y_big = run(x)
+    y_small = torch.cat([run(x[i:i + 97].contiguous()) for i in range(0, B, 97)])
+    assert torch.equal(y_big, y_small)
+    # training mode (saved q, k, v, o, lse) through autograd: gradients agree bit for bit as well
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    g = _rand(rs, B, L, C).float().cuda()
+
+    def run_grad(xs):
+        return ops.AttnBlockFn.apply(xs, d["norm1.weight"], d["norm1.bias"], d["attn.qkv_proj.to_q.weight"],
+                                     d["attn.qkv_proj.to_q.bias"], d["attn.qkv_proj.to_kv.weight"],
+                                     d["attn.qkv_proj.to_kv.bias"], d["attn.proj.weight"], d["attn.proj.bias"],
+                                     table, H, W, (L - W) // 2 if W else 0, ops.RL_F_PRENORM | ops.RL_F_RESIDUAL)
+
+    run_grad(xa).backward(g)
+    for i in range(0, B, 97):
+        run_grad(xb[i:i + 97]).backward(g[i:i + 97])
+    assert torch.equal(xa.grad, xb.grad)
+
+
 def test_attn_plain_msattention(ops):
     """MSAttention.forward alone: no pre-norm, no residual (flags = 0)."""
     rs = np.random.RandomState(7)

@@ -100,6 +100,7 @@ def load():
     lib.ralenet_launch_count.restype = ctypes.c_int64
     lib.ralenet_launch_count.argtypes = [ctypes.c_int32]
     lib.ralenet_check_device.argtypes = [ctypes.c_int]
+    lib.ralenet_snr_mix.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int32] * 2 + [ctypes.c_void_p]
     for name in ("ralenet_adam", "ralenet_adam_dev"):
         getattr(lib, name).argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64] + [ctypes.c_float] * 4 + [
             ctypes.c_int32 if name == "ralenet_adam" else ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p]

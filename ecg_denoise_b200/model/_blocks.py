@@ -55,6 +55,22 @@ class DropPath(nn.Module):
         return x
 
 
+class eca_layer_1d(nn.Module):
+    """Efficient channel attention on (B, L, C) tokens (reference model/transformer.py:100-113): the Conv1d(1,1,k)
+    runs over the channel axis of the per-window channel means.  `res` fuses the block residual."""
+
+    def __init__(self, channels, k_size=3) -> None:
+        super().__init__()
+        self.avg_pool = nn.AdaptiveAvgPool1d(1)
+        self.conv = nn.Conv1d(1, 1, kernel_size=k_size, padding=(k_size - 1) // 2, bias=False)
+        self.sigmoid = nn.Sigmoid()
+        self.channels = channels
+        self.k_size = k_size
+
+    def forward(self, x, res=None):
+        return ops.EcaFn.apply(x, self.conv.weight, res)
+
+
 class Mlp(nn.Module):
     """Feed-forward with optional local enhancement (reference model/transformer.py:118-161)."""
     _LE_DEFAULT = False
@@ -66,8 +82,6 @@ class Mlp(nn.Module):
             local_enhence = self._LE_DEFAULT
         out_features = out_features or in_features
         hidden_features = hidden_features or in_features
-        if use_eca:
-            _unsupported("eca_layer_1d (use_eca=True)")
         if act_layer is not nn.GELU:
             _unsupported(f"activation {act_layer}")
         if drop:
@@ -76,7 +90,9 @@ class Mlp(nn.Module):
             _unsupported("Mlp with hidden != 4*in or out != in")
         self.local_enhence = local_enhence
         self.use_partial = use_partial
-        self.eca = nn.Identity()
+        self.use_eca = bool(use_eca)
+        # registration order of the reference (:134-140): eca, fc1, act, fc2, drop, leconv
+        self.eca = eca_layer_1d(out_features) if use_eca else nn.Identity()
         self.fc1 = nn.Linear(in_features, hidden_features)
         self.act = act_layer()
         self.fc2 = nn.Linear(hidden_features, out_features)
@@ -97,8 +113,9 @@ class Mlp(nn.Module):
 
     def forward(self, x):
         mode, lew = self._le()
-        return ops.FFNBlockFn.apply(x, None, None, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
-                                    lew, None, mode, 0)
+        y = ops.FFNBlockFn.apply(x, None, None, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+                                 lew, None, mode, 0)
+        return self.eca(y) if self.use_eca else y
 
 
 class AbsPositionalEncoding(nn.Module):
@@ -214,13 +231,18 @@ class TransformerBlock(nn.Module):
         """feed-forward branch WITHOUT the residual (reference :392-395)."""
         m = self.mlp
         mode, lew = m._le()
-        return ops.FFNBlockFn.apply(x, self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight,
-                                    m.fc2.bias, lew, None, mode, ops.RL_F_PRENORM)
+        y = ops.FFNBlockFn.apply(x, self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight,
+                                 m.fc2.bias, lew, None, mode, ops.RL_F_PRENORM)
+        return m.eca(y) if m.use_eca else y
 
     def forward(self, x, mask=None):
         x = self.attn._run(x, mask, self.norm1, ops.RL_F_PRENORM | ops.RL_F_RESIDUAL)
         m = self.mlp
         mode, lew = m._le()
+        if m.use_eca:      # the channel gate sits between fc2 and the residual (reference :158, :410)
+            y = ops.FFNBlockFn.apply(x, self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight,
+                                     m.fc2.bias, lew, None, mode, ops.RL_F_PRENORM)
+            return m.eca(y, res=x)
         return ops.FFNBlockFn.apply(x, self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight,
                                     m.fc2.bias, lew, None, mode, ops.RL_F_PRENORM | ops.RL_F_RESIDUAL)
 

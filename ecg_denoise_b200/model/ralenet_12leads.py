@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch.nn as nn
 
 from .. import ops
-from ._blocks import (AbsPositionalEncoding, BasicLayer, DropPath, LinearProjection, Mlp, MSAttention,  # noqa: F401
+from ._blocks import (eca_layer_1d, AbsPositionalEncoding, BasicLayer, DropPath, LinearProjection, Mlp, MSAttention,  # noqa: F401
                       PartialConv_1d, PatchMerging, PatchSeparate, RelativePositionEmbedding, TransformerBlock,
                       _RalenetBase, build_ralenet, mask_fill)
 

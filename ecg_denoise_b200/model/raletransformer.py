@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch.nn as nn
 
 from . import _blocks as _b
-from ._blocks import (AbsPositionalEncoding, DropPath, LinearProjection, MSAttention, PartialConv_1d,  # noqa: F401
+from ._blocks import (eca_layer_1d, AbsPositionalEncoding, DropPath, LinearProjection, MSAttention, PartialConv_1d,  # noqa: F401
                       PatchMerging, PatchSeparate, _RalenetBase, build_ralenet)
 
 

@@ -311,6 +311,57 @@ class Conv1dFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+class EcaFn(torch.autograd.Function):
+    """eca_layer_1d.forward (model/transformer.py:109-113) on (B, L, C) tokens, optionally fused with the block
+    residual: y = x * sigmoid(conv_k(mean_t x)) (+ res)."""
+
+    @staticmethod
+    def forward(ctx, x, w, res):
+        x = _chk(x, "x")
+        B, L, C = x.shape
+        K = w.numel()
+        res = _chk(res, "res") if res is not None else None
+        y = torch.empty_like(x)
+        s = torch.empty(B, C, device=x.device, dtype=torch.float32)
+        a = _fill("rl_eca_fwd_args", B=B, L=L, C=C, K=K, x=x, res=_p(res), w=w, y=y, s=s)
+        _lib.call("ralenet_eca_fwd", a, _stream())
+        ctx.save_for_backward(x, w, s)
+        ctx.has_res = res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, s = ctx.saved_tensors
+        B, L, C = x.shape
+        g = _chk(g, "grad")
+        nig = ctx.needs_input_grad
+        dx = torch.empty_like(x)
+        d_w = torch.zeros_like(w) if nig[1] else None
+        a = _fill("rl_eca_bwd_args", B=B, L=L, C=C, K=w.numel(), g=g, x=x, w=w, s=s, dx=dx, d_w=_p(d_w))
+        _lib.call("ralenet_eca_bwd", a, _stream())
+        return dx if nig[0] else None, d_w, (g if (ctx.has_res and nig[2]) else None)
+
+
+def snr_mix(data: torch.Tensor, noise: torch.Tensor, snr_db) -> torch.Tensor:
+    """single_snr_noise_add (local_utils/local_utils.py:176-192) for a batch of windows on the GPU:
+    out[b] = data[b] + noise[b] * sqrt(mean(data[b]**2) / 10**(snr_db[b]/10) / mean(noise[b]**2)), the means over
+    all leads and samples of window b.  `snr_db`: float or (B,) tensor."""
+    data, noise = _chk(data, "data"), _chk(noise, "noise")
+    if data.shape != noise.shape:
+        raise _lib.RalenetError(f"snr_mix: data {tuple(data.shape)} and noise {tuple(noise.shape)} differ")
+    B = data.shape[0]
+    if not isinstance(snr_db, torch.Tensor):
+        snr_db = torch.full((B,), float(snr_db), device=data.device, dtype=torch.float32)
+    snr_db = _chk(snr_db, "snr_db")
+    if snr_db.numel() != B:
+        raise _lib.RalenetError(f"snr_mix: snr_db has {snr_db.numel()} entries for {B} windows")
+    out = torch.empty_like(data)
+    _lib.check(_lib.load().ralenet_snr_mix(ctypes.c_void_p(data.data_ptr()), ctypes.c_void_p(noise.data_ptr()),
+                                           ctypes.c_void_p(snr_db.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                           B, data.numel() // B, ctypes.c_void_p(_stream())))
+    return out
+
+
 def mse_loss_metrics(pred: torch.Tensor, target: torch.Tensor, want_grad: bool = True, gscale: float = 1.0,
                      global_numel: Optional[int] = None, weight: Optional[torch.Tensor] = None):
     """Fused F.mse_loss (denoise_train.py:53) + its gradient + per-window RMSE / SNR

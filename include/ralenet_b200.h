@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RL_ABI_VERSION 1
+#define RL_ABI_VERSION 2
 
 enum {
   RL_OK = 0,
@@ -328,6 +328,33 @@ int ralenet_window_gather(const float* x, const float* stats, float* win, int32_
                           int32_t W, int32_t stride, void* stream);
 int ralenet_window_scatter(const float* win, const float* x, const float* stats, float* y, int32_t R, int32_t C,
                            int64_t T, int32_t W, int32_t stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Efficient channel attention on the feed-forward output (eca_layer_1d, model/transformer.py:100-113, used by
+ * Mlp.forward :158 when use_eca=True):   s[b,c] = sigmoid( sum_k w[k] * mean_t x[b,t,c+k-(K-1)/2] )  (zero padded
+ * over the channel axis),  y = x * s  (+ res: the block residual, fused).  x, y, res: [B,L,C]; w: [K] (K odd <= 15,
+ * Conv1d(1,1,K,bias=False)); s: [B,C] saved for backward (may be NULL in forward-only use).  256 % C == 0.
+ * backward: dx = g*s + dm/L with dm the adjoint of the channel convolution; d_w (+=) may be NULL;
+ * the gradient w.r.t. res is g itself (caller's business).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t B, L, C, K;
+  const float* x; const float* res; const float* w;
+  float* y; float* s;
+} rl_eca_fwd_args;
+typedef struct {
+  int32_t B, L, C, K;
+  const float* g; const float* x; const float* w; const float* s;
+  float* dx; float* d_w;
+} rl_eca_bwd_args;
+int ralenet_eca_fwd(const rl_eca_fwd_args* a, void* stream);
+int ralenet_eca_bwd(const rl_eca_bwd_args* a, void* stream);
+
+/* SNR-targeted noise mixing (single_snr_noise_add, local_utils/local_utils.py:176-192), one window per CTA:
+ *   out[b] = data[b] + noise[b] * sqrt( mean(data[b]^2) / 10^(snr_db[b]/10) / mean(noise[b]^2) )
+ * with the means over all `per` elements (leads x samples) of window b.  data, noise, out: [B][per]; snr_db: [B]. */
+int ralenet_snr_mix(const float* data, const float* noise, const float* snr_db, float* out, int32_t B, int32_t per,
+                    void* stream);
 
 /* Weight-gradient GEMM over the token dimension (used by every *_bwd above; exported for benchmarks):
  *   dW[n*K + k] += sum_m dY[m*ldy + n] * X[m*ldx + k],   db[n] += sum_m dY[m*ldy + n]   (db may be NULL) */

@@ -600,3 +600,70 @@ def windows_to_records(win: Tensor, x: Tensor, stats, stride: int = 256) -> Tens
     mean, std = stats
     y = torch.where(cnt > 0, acc / cnt.clamp(min=1) * std + mean, x)
     return y
+
+
+# ------------------------------------------------------------------------------------------------
+# Section 8f extras: efficient channel attention and SNR-targeted noise mixing
+def eca_fwd(x: Tensor, w: Tensor, res: Optional[Tensor] = None):
+    """eca_layer_1d.forward on (B, L, C) tokens (model/transformer.py:109-113): avg-pool over the tokens, Conv1d(1,1,k)
+    over the channel axis (zero padded, no bias), sigmoid, channel-wise scaling; `res` = the block residual that
+    TransformerBlock.forward adds afterwards (:410).  Returns (y, saved)."""
+    B, L, C = x.shape
+    K = w.numel()
+    P = (K - 1) // 2
+    m = x.mean(dim=1)                                               # (B, C)
+    mp = torch.zeros(B, C + 2 * P, dtype=x.dtype)
+    mp[:, P:P + C] = m
+    z = sum(w.reshape(-1)[k] * mp[:, k:k + C] for k in range(K))    # z[c] = sum_k w[k] m[c + k - P]
+    s = torch.sigmoid(z)
+    y = x * s[:, None, :]
+    if res is not None:
+        y = y + res
+    return y, (x, m, s)
+
+
+def eca_bwd(g: Tensor, saved, w: Tensor):
+    """gradients of eca_fwd w.r.t. x and w (the gradient w.r.t. res is g)."""
+    x, m, s = saved
+    B, L, C = x.shape
+    K = w.numel()
+    P = (K - 1) // 2
+    ds = (g * x).sum(dim=1)                                         # (B, C)
+    dz = ds * s * (1 - s)
+    dzp = torch.zeros(B, C + 2 * P, dtype=x.dtype)
+    dzp[:, P:P + C] = dz
+    mp = torch.zeros(B, C + 2 * P, dtype=x.dtype)
+    mp[:, P:P + C] = m
+    # dm[c'] = sum_k w[k] dz[c' - k + P];  dw[k] = sum_{b,c} dz[c] m[c + k - P]
+    dm = sum(w.reshape(-1)[k] * dzp[:, 2 * P - k:2 * P - k + C] for k in range(K))
+    dw = torch.stack([(dz * mp[:, k:k + C]).sum() for k in range(K)]).reshape(w.shape)
+    dx = g * s[:, None, :] + dm[:, None, :] / L
+    return dx, dw
+
+
+def snr_mix(data: Tensor, noise: Tensor, snr_db: Tensor) -> Tensor:
+    """single_snr_noise_add (local_utils/local_utils.py:176-192) per window of a batch: energies are means over ALL
+    elements of a window (leads and samples), scale = sqrt(signal_energy / 10**(snr/10) / noise_energy)."""
+    B = data.shape[0]
+    d, n = data.reshape(B, -1), noise.reshape(B, -1)
+    ps = (d.abs() ** 2).mean(dim=1)
+    pn = (n.abs() ** 2).mean(dim=1)
+    target = ps / (10 ** (snr_db.to(data.dtype) / 10))
+    scale = torch.sqrt(target / pn)
+    return data + noise * scale.reshape(B, *([1] * (data.dim() - 1)))
+
+
+def ffn_eca_block_fwd(x1: Tensor, p: Dict[str, Tensor]):
+    """feed-forward half of a TransformerBlock built with use_eca=True: x1 + eca(Mlp(LN2(x1)))
+    (model/transformer.py:158, :392-395, :410); p carries "mlp.eca.conv.weight"."""
+    y_res, saved = ffn_block_fwd(x1, p)
+    y, esaved = eca_fwd(y_res - x1, p["mlp.eca.conv.weight"], res=x1)
+    return y, (saved, esaved)
+
+
+def ffn_eca_block_bwd(g: Tensor, saved, p: Dict[str, Tensor]):
+    fsaved, esaved = saved
+    d, dw = eca_bwd(g, esaved, p["mlp.eca.conv.weight"])
+    dx_with_res, grads = ffn_block_bwd(d, fsaved, p)          # = d + dz
+    grads["mlp.eca.conv.weight"] = dw
+    return g + (dx_with_res - d), grads

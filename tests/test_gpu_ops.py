@@ -346,3 +346,58 @@ def test_errors_are_loud(ops):
     with pytest.raises(_lib.RalenetError):
         ops.PatchFn.apply(torch.zeros(1, 100, 8, device="cuda"), torch.ones(16, device="cuda"),
                           torch.zeros(16, device="cuda"), torch.zeros(16, 16, device="cuda"), None, 0)  # bad shape
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY.md section 8f extras: efficient channel attention, SNR-targeted noise mixing
+def _extras():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "extras_golden.npz"))
+
+
+@pytest.mark.parametrize("k", [3, 5])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_eca_vs_reference_golden(ops, k, with_res):
+    gold = _extras()
+    x, w, gy = (torch.from_numpy(gold[f"eca{k}/{n}"]) for n in ("x", "w", "gy"))
+    xt, wt = _dev(x), _dev(w)
+    res = _dev(_rand(np.random.RandomState(k), *x.shape)) if with_res else None
+    y = ops.EcaFn.apply(xt, wt, res)
+    y_ref = torch.from_numpy(gold[f"eca{k}/y"]) + (res.detach().double().cpu() if with_res else 0)
+    tag = f"eca/k{k}/{'res' if with_res else 'plain'}"
+    _cmp(tag + "/y", y, y_ref)
+    y.backward(gy.float().cuda())
+    _cmp(tag + "/dx", xt.grad, torch.from_numpy(gold[f"eca{k}/dx"]))
+    _cmp(tag + "/dw", wt.grad, torch.from_numpy(gold[f"eca{k}/dw"]))
+    if with_res:
+        _cmp(tag + "/dres", res.grad, gy)
+
+
+def test_transformer_block_with_eca_vs_reference_golden():
+    """TransformerBlock(use_eca=True) through the module mirror: the gate sits between fc2 and the residual."""
+    from ecg_denoise_b200.model.transformer import TransformerBlock
+    gold = _extras()
+    blk = TransformerBlock(32, 8, local_enhence=True, use_eca=True)
+    sd = {str(k): torch.from_numpy(gold[f"blk/p/{k}"]).float() for k in gold["blk/keys"]}
+    blk.load_state_dict(sd, strict=True)
+    blk = blk.cuda()
+    x = _dev(torch.from_numpy(gold["blk/x"]))
+    y = blk(x)
+    _cmp("eca_block/y", y, torch.from_numpy(gold["blk/y"]))
+    y.backward(torch.from_numpy(gold["blk/gy"]).float().cuda())
+    _cmp("eca_block/dx", x.grad, torch.from_numpy(gold["blk/dx"]))
+    for k, p in blk.named_parameters():
+        _cmp(f"eca_block/d_{k}", p.grad, torch.from_numpy(gold[f"blk/g/{k}"]))
+
+
+def test_snr_mix_vs_reference_golden(ops):
+    gold = _extras()
+    data, noise, snr = (torch.from_numpy(gold[f"snr/{n}"]).cuda() for n in ("data", "noise", "snr"))
+    out = ops.snr_mix(data, noise, snr)
+    _cmp("snr_mix/out", out, torch.from_numpy(gold["snr/out"]), rtol=1e-5)
+    # scalar SNR for the whole batch, and a benchmark-sized batch: the mixed windows have the requested SNR
+    rs = np.random.RandomState(11)
+    d = _rand(rs, 4096, 2, 256).float().cuda()
+    n = _rand(rs, 4096, 2, 256, scale=0.3).float().cuda()
+    o = ops.snr_mix(d, n, -2.0)
+    got = 10 * torch.log10((d.double() ** 2).mean((1, 2)) / ((o.double() - d.double()) ** 2).mean((1, 2)))
+    assert torch.allclose(got, torch.full_like(got, -2.0), atol=1e-3)

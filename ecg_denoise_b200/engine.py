@@ -13,6 +13,7 @@ like autograd does), so a training step costs no per-parameter Python work.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Callable, List, Optional
 
 import torch
@@ -281,7 +282,7 @@ class FusedTrainer:
     """
 
     def __init__(self, net: nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 process_group=None, use_graph: bool = False):
+                 process_group=None, use_graph: bool = False, graph_collectives: Optional[bool] = None):
         from . import ops
         self.ops = ops
         self.net = net
@@ -292,6 +293,9 @@ class FusedTrainer:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self.use_graph = use_graph
+        # capture the NCCL all-reduces inside the step's CUDA graph (default; RALENET_GRAPH_NCCL=0 keeps them outside)
+        self.graph_collectives = (os.environ.get("RALENET_GRAPH_NCCL", "1") != "0") if graph_collectives is None \
+            else bool(graph_collectives)
         self.graph = None
         self.m = self.v = self.step_dev = None
         self._static = None
@@ -358,10 +362,17 @@ class FusedTrainer:
 
         if self.world == 1:
             return [("compute", lambda: (seg_a(), seg_b(), seg_c(), seg_d()))]
+
+        def ar_bwd_stats():
+            # the 16 BN backward sums and the loss share one all-reduce (slot 48 of bn_stats is free)
+            plan.bn_stats[48:49].copy_(self._res[0])
+            self._allreduce(plan.bn_stats[32:49])
+            self._res[0].copy_(plan.bn_stats[48:49])
+
         return [("compute", seg_a), ("collective", lambda: self._allreduce(plan.bn_stats[:17])),
-                ("compute", seg_b), ("collective", lambda: self._allreduce(plan.bn_stats[32:48])),
+                ("compute", seg_b), ("collective", ar_bwd_stats),
                 ("compute", seg_c),
-                ("collective", lambda: (self._allreduce(plan.flat_grad), self._allreduce(self._res[0]))),
+                ("collective", lambda: self._allreduce(plan.flat_grad)),
                 ("compute", seg_d)]
 
     def _step_impl(self, x, target):
@@ -399,17 +410,33 @@ class FusedTrainer:
             # undo the warm-up step so that capture + replay applies exactly one update per call
             self.plan.flat.copy_(snap[0]); self.m.copy_(snap[1]); self.v.copy_(snap[2]); self.step_dev.copy_(snap[3])
             bn.running_mean.copy_(snap[4]); bn.running_var.copy_(snap[5]); bn.num_batches_tracked.copy_(snap[6])
-            plan = []
-            pool = None
-            for kind, fn in self._pieces(sx, st_):
-                if kind == "collective":
-                    plan.append((None, fn))
-                    continue
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
-                    fn()
-                pool = g.pool()
-                plan.append((g, None))
+            plan = None
+            if self.world > 1 and self.graph_collectives:
+                # one graph for the whole step, NCCL all-reduces captured as graph nodes (no host round trip and
+                # no launch gap between the segments); falls back to the segmented form if capture is refused
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                        for _, fn in self._pieces(sx, st_):
+                            fn()
+                    plan = [(g, None)]
+                except Exception as e:      # noqa: BLE001 -- any capture failure means "use the segmented form"
+                    import warnings
+                    warnings.warn(f"FusedTrainer: NCCL graph capture failed ({e}); using segmented graphs")
+                    torch.cuda.synchronize()
+                    plan = None
+            if plan is None:
+                plan = []
+                pool = None
+                for kind, fn in self._pieces(sx, st_):
+                    if kind == "collective":
+                        plan.append((None, fn))
+                        continue
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
+                        fn()
+                    pool = g.pool()
+                    plan.append((g, None))
             self.graph = plan
             self._graph_out = self._res
             # capture does not execute: the replay below performs the step

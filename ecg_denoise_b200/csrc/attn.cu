@@ -200,12 +200,27 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   }
   __syncthreads();
   RL_TS(attn, 3);
-  // 3. D[h,i] = do_i . o_i
+  // 3. per-window power-of-two scale that puts max|do| at 2^6 (the single-pass core carries its operands as fp16
+  //    hi/lo pairs; gradients are ~1e-6 and would underflow unscaled), then D[h,i] = do_i . o_i (scaled alike)
+  float do_scale;
+  {
+    __shared__ float s_amax[RL_NT / 32];
+    float am = 0.f;
+    for (int i = tid; i < LC; i += RL_NT) am = fmaxf(am, fabsf(sdo[(i / C) * LDC + (i % C)]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+    if ((tid & 31) == 0) s_amax[tid >> 5] = am;
+    __syncthreads();
+    am = s_amax[0];
+#pragma unroll
+    for (int w = 1; w < RL_NT / 32; ++w) am = fmaxf(am, s_amax[w]);
+    do_scale = (am > 0.f && am < 3e38f) ? exp2f(6.f - ceilf(log2f(am))) : 1.f;
+  }
   for (int item = tid; item < H * L; item += RL_NT) {
     const int i = item % L, h = item / L;
     const float4 d4 = *reinterpret_cast<const float4*>(sdo + i * LDC + 4 * h);
     const float4 o4 = *reinterpret_cast<const float4*>(sdk + i * LDC + 4 * h);
-    sD[item] = d4.x * o4.x + d4.y * o4.y + d4.z * o4.z + d4.w * o4.w;
+    sD[item] = do_scale * (d4.x * o4.x + d4.y * o4.y + d4.z * o4.z + d4.w * o4.w);
   }
   __syncthreads();
 
@@ -214,12 +229,18 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   if (FW) __syncthreads();
   RL_TS(attn, 4);
 
-  // 4. attention core backward on the tensor cores (attn_core.cuh): a query-major pass for dq (+ the R-wave table
-  //    gradient) and a key-major pass for dk, dv; p is recomputed from the saved log-sum-exp.
-  //    (sdk held o, last read in step 3 before a barrier)
-  attn_core_bwd_dq<C, L>(sq, sk, sv, sdo, sD, sLse, sdq, stab, stabg, a.d_table != nullptr, W, c0);
+  // 4. attention core backward on the tensor cores (attn_core.cuh), single pass: q, k, v, do are re-packed in place
+  //    as fp16 hi/lo pairs, one warp per (head, 16-key tile) walks the queries once; p is recomputed from the saved
+  //    log-sum-exp; dq partial sums meet in shared-memory reds (sdq held g, sdk held o: both dead by now).
+  to_row_form<C>(sq, LDC, L, 0.5f * RL_LOG2E);
+  to_row_form<C>(sk, LDC, L, 1.f);
+  to_row_form<C>(sv, LDC, L, 1.f);
+  to_row_form<C>(sdo, LDC, L, do_scale);
+  for (int i = tid; i < LP; i += RL_NT) sdq[i] = 0.f;
+  __syncthreads();
   RL_TS(attn, 5);
-  attn_core_bwd_dkv<C, L>(sq, sk, sv, sdo, sD, sLse, sdk, sdv, stab, W, c0);
+  attn_core_bwd_single<C, L>(sq, sk, sv, sdo, sD, sLse, sdq, sdk, sdv, stab, stabg, a.d_table != nullptr, W, c0,
+                             1.0f / do_scale);
   __syncthreads();
   RL_TS(attn, 6);
 

@@ -292,3 +292,187 @@ __device__ __forceinline__ void attn_core_bwd_dkv(const float* sq, const float* 
     }
   }
 }
+
+// =============================================================================================
+// Single-pass backward core on fp16 hi/lo PAIRS (m16n8k16).
+//
+// Every operand x is carried as x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits, more than the
+// truncated-tf32 split above (gradients are pre-scaled per window by a power of two so that fp16 cannot underflow).
+// Four values are stored as four packed words  [hi(d0,d1) | hi(d2,d3) | lo(d0,d1) | lo(d2,d3)]  in the 16 bytes the
+// fp32 head slice occupied ("row form": q, k, v, dO converted IN PLACE), and the 16 k-slots of one m16n8k16 MMA hold
+// the four cross products of a head_dim-4 contraction:
+//      slots 0-3: a_hi b_hi   4-7: a_hi b_lo   8-11: a_lo b_hi   12-15: a_lo b_lo        (one MMA = full product)
+// One warp owns a (head, 16-key tile) and walks the queries once, 16 at a time:
+//      S^T  = k q^T, dP^T = v dO^T                          (2 MMAs per 8 queries; rows = keys, cols = queries)
+//      p    = exp2(S^T - lse), dS^T = p (dP^T - D)
+//      dv  += P^T dO, dk += dS^T q                           (A = the accumulator fragments re-packed as hi / lo pairs)
+//      dq^T = k^T dS^T                                       (B = dS^T pairs transposed in registers with movmatrix)
+// The dq partial sums of the key tiles of one head are added into shared memory WITHOUT atomics (fp32 shared atomics
+// are CAS loops): the warps that work on the same head walk the query blocks in a rotated order -- warp with key tile
+// jt visits query block (jt + step) mod NQB -- and meet at a named barrier after every step, so at any time each
+// query block of a head has exactly one writer.
+// so S and dP are computed once instead of twice and no operand is split inside the loop.
+#include <cuda_fp16.h>
+
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+// (x0, x1) -> packed fp16 pairs hi = (fp16(x0), fp16(x1)), lo = the fp16 remainders; x0 in the low half
+__device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const __half2 l = __floats2half2_rn(x0 - __low2float(h), x1 - __high2float(h));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// convert the [rows][C] fp32 array (stride ld) to row form in place, scaling by `scale`
+template <int C>
+__device__ __forceinline__ void to_row_form(float* s, int ld, int rows, float scale) {
+  constexpr int H = C / RL_HD;
+  for (int i = threadIdx.x; i < rows * H; i += RL_NT) {
+    float* p = s + (i / H) * ld + 4 * (i % H);
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    uint4 o;
+    split_h2(v.x * scale, v.y * scale, o.x, o.z);
+    split_h2(v.z * scale, v.w * scale, o.y, o.w);
+    *reinterpret_cast<uint4*>(p) = o;
+  }
+}
+// one register of a "pairs along rows" operand built from two row-form words: the fp16 of dim-slot `slot`
+// (0-3: hi of dims 0-3, 4-7: lo) of rows r and r+1 (row r in the low half)
+__device__ __forceinline__ uint32_t col_pair(const uint32_t* base, int ld, int r, int slot) {
+  const int word = (slot >> 2) * 2 + ((slot & 3) >> 1);
+  const uint32_t a = base[r * ld + word], b = base[(r + 1) * ld + word];
+  return (slot & 1) ? __byte_perm(a, b, 0x7632) : __byte_perm(a, b, 0x5410);
+}
+
+// QP (pre-scaled by 0.5 log2e), KP, VP, DP (pre-scaled by do_scale): row-form arrays; sD pre-scaled by do_scale;
+// sdq: fp32, ZEROED, receives 0.5 dS k (plain read-modify-write, see above); sdk, sdv: fp32 outputs.
+template <int C, int L>
+__device__ __forceinline__ void attn_core_bwd_single(const float* QPf, const float* KPf, const float* VPf,
+                                                     const float* DPf, const float* sD, const float* sLse, float* sdq,
+                                                     float* sdk, float* sdv, const float* stab, float* stabg,
+                                                     bool want_tab, int W, int c0, float inv_do_scale) {
+  constexpr int H = C / RL_HD, LDC = ld_mk(C), NW = RL_NT / 32;
+  constexpr int JT = L / 16, NITEM = H * JT;
+  static_assert(NITEM % NW == 0 && (JT >= NW ? JT % NW == 0 : NW % JT == 0), "bwd core: items must tile the warps");
+  constexpr int GW = (JT < NW) ? JT : NW;                       // warps that share a head within one round
+  const uint32_t* QP = reinterpret_cast<const uint32_t*>(QPf);
+  const uint32_t* KP = reinterpret_cast<const uint32_t*>(KPf);
+  const uint32_t* VP = reinterpret_cast<const uint32_t*>(VPf);
+  const uint32_t* DP = reinterpret_cast<const uint32_t*>(DPf);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const float f_dq = 0.5f * inv_do_scale;                       // dq = 0.5 dS k
+  const float f_dk = inv_do_scale / RL_LOG2E;                   // dk = 0.5 dS q, q carried as q * 0.5 log2e
+#pragma unroll 1
+  for (int item = warp; item < NITEM; item += NW) {
+    const int h = item / JT, j0 = (item % JT) * 16;
+    uint32_t ka[4], va[4], kt[4];
+    {
+      const int o0 = (j0 + g) * LDC + 4 * h + (t & 1);
+      ka[0] = KP[o0]; ka[1] = KP[o0 + 8 * LDC]; ka[2] = KP[o0 + 2]; ka[3] = KP[o0 + 8 * LDC + 2];
+      va[0] = VP[o0]; va[1] = VP[o0 + 8 * LDC]; va[2] = VP[o0 + 2]; va[3] = VP[o0 + 8 * LDC + 2];
+      // k^T for dq^T = k^T dS^T: rows = dim slots (g < 8), k = keys (2t, 2t+1) and (2t+8, 2t+9); rows 8-15 unused
+      kt[0] = col_pair(KP + 4 * h, LDC, j0 + 2 * t, g);
+      kt[2] = col_pair(KP + 4 * h, LDC, j0 + 2 * t + 8, g);
+      kt[1] = kt[3] = 0u;
+    }
+    float ak[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool kcen = (W > 0) && (j0 + 16 > c0) && (j0 < c0 + W);
+    const float* lsep = sLse + h * L + 2 * t;
+    const float* Dp = sD + h * L + 2 * t;
+#pragma unroll 1
+    for (int step = 0; step < JT; ++step) {
+      const int i0 = (((item % JT) + step) % JT) * 16;          // rotated walk: one writer per query block and step
+      uint32_t pah[4], pal[4], dah[4], dal[4];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int ib = i0 + 8 * hf;
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+          const uint32_t bq = QP[(ib + g) * LDC + 4 * h + t], bd = DP[(ib + g) * LDC + 4 * h + t];
+          const uint32_t b0[2] = {bq, bq}, b1[2] = {bd, bd};
+          mma_f16(s, ka, b0);
+          mma_f16(dp, va, b1);
+        }
+        const bool cen = kcen && (ib + 8 > c0) && (ib < c0 + W);
+        if (cen) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = ib + 2 * t + (e & 1), j = j0 + g + 8 * (e >> 1);
+            if ((unsigned)(i - c0) < (unsigned)W && (unsigned)(j - c0) < (unsigned)W) s[e] += stab[(i - j + W - 1) * H + h];
+          }
+        }
+        const float2 ls = *reinterpret_cast<const float2*>(lsep + ib);
+        const float2 Dd = *reinterpret_cast<const float2*>(Dp + ib);
+        float p[4], ds[4];
+        p[0] = fast_ex2(s[0] - ls.x);
+        p[1] = fast_ex2(s[1] - ls.y);
+        p[2] = fast_ex2(s[2] - ls.x);
+        p[3] = fast_ex2(s[3] - ls.y);
+        ds[0] = p[0] * (dp[0] - Dd.x);
+        ds[1] = p[1] * (dp[1] - Dd.y);
+        ds[2] = p[2] * (dp[2] - Dd.x);
+        ds[3] = p[3] * (dp[3] - Dd.y);
+        if (cen && want_tab) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = ib + 2 * t + (e & 1), j = j0 + g + 8 * (e >> 1);
+            if ((unsigned)(i - c0) < (unsigned)W && (unsigned)(j - c0) < (unsigned)W)
+              atomicAdd(&stabg[(i - j + W - 1) * H + h], ds[e] * inv_do_scale);
+          }
+        }
+        // accumulator fragments -> A fragments of the query contraction (rows = keys, k = the queries of this half)
+        split_h2(p[0], p[1], pah[2 * hf], pal[2 * hf]);
+        split_h2(p[2], p[3], pah[2 * hf + 1], pal[2 * hf + 1]);
+        split_h2(ds[0], ds[1], dah[2 * hf], dal[2 * hf]);
+        split_h2(ds[2], ds[3], dah[2 * hf + 1], dal[2 * hf + 1]);
+        // dq^T[dim slot][query] = sum_keys k^T dS^T: transpose the 8x8 (key, query) pair blocks into B fragments
+        {
+          const uint32_t bh[2] = {movmatrix_trans(dah[2 * hf]), movmatrix_trans(dah[2 * hf + 1])};
+          const uint32_t bl[2] = {movmatrix_trans(dal[2 * hf]), movmatrix_trans(dal[2 * hf + 1])};
+          float dq[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_f16(dq, kt, bh);
+          mma_f16(dq, kt, bl);
+          const float v0 = dq[0] + __shfl_xor_sync(0xffffffffu, dq[0], 16);     // hi-slot rows + lo-slot rows
+          const float v1 = dq[1] + __shfl_xor_sync(0xffffffffu, dq[1], 16);
+          // lanes g < 4 own (query 2t, dim g), lanes g >= 4 own (query 2t+1, dim g-4); exclusive by construction
+          float* dst = sdq + (ib + 2 * t + (g >> 2)) * LDC + 4 * h + (g & 3);
+          *dst += ((g < 4) ? v0 : v1) * f_dq;
+        }
+      }
+      // dv += P^T dO, dk += dS^T q over the 16 queries: B = (query pairs) x (dim slots)
+      {
+        const uint32_t bd[2] = {col_pair(DP + 4 * h, LDC, i0 + 2 * t, g), col_pair(DP + 4 * h, LDC, i0 + 2 * t + 8, g)};
+        const uint32_t bq[2] = {col_pair(QP + 4 * h, LDC, i0 + 2 * t, g), col_pair(QP + 4 * h, LDC, i0 + 2 * t + 8, g)};
+        mma_f16(av, pah, bd);
+        mma_f16(ak, dah, bq);
+        mma_f16(av, pal, bd);
+        mma_f16(ak, dal, bq);
+      }
+      if (GW > 1) {                                             // the GW warps of this head move to their next block
+        if (GW == NW) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / GW), "n"(GW * 32) : "memory");
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ak[e] += __shfl_xor_sync(0xffffffffu, ak[e], 2);          // hi dim slots (t = 0, 1) + lo dim slots (t = 2, 3)
+      av[e] += __shfl_xor_sync(0xffffffffu, av[e], 2);
+    }
+    if (t < 2) {
+      const int off = (j0 + g) * LDC + 4 * h + 2 * t;
+      *reinterpret_cast<float2*>(sdk + off) = make_float2(f_dk * ak[0], f_dk * ak[1]);
+      *reinterpret_cast<float2*>(sdk + off + 8 * LDC) = make_float2(f_dk * ak[2], f_dk * ak[3]);
+      *reinterpret_cast<float2*>(sdv + off) = make_float2(inv_do_scale * av[0], inv_do_scale * av[1]);
+      *reinterpret_cast<float2*>(sdv + off + 8 * LDC) = make_float2(inv_do_scale * av[2], inv_do_scale * av[3]);
+    }
+  }
+}

@@ -13,8 +13,8 @@ lib = _lib.load()
 lib.ralenet_debug_trace_read_attn.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 FWD = ["prefetch+pdl", "PE+LN", "qkv GEMM", "store qkv", "core", "store o", "proj GEMM", "epilogue"]
-BWD = ["prefetch+pdl", "stage", "do GEMM", "D + wgrad(wp)", "core dq", "core dkv", "dqkv scratch", "du GEMM", "LN bwd",
-       "wgrad(q,kv)+table"]
+BWD = ["prefetch+pdl", "stage", "do GEMM", "amax + D + wgrad(wp)", "repack fp16 pairs", "core (single pass)", "dqkv scratch",
+       "du GEMM", "LN bwd", "wgrad(q,kv)+table"]
 
 
 def read(n):

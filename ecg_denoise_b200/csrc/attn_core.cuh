@@ -395,7 +395,10 @@ __device__ __forceinline__ void attn_core_bwd_single(const float* QPf, const flo
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int ib = i0 + 8 * hf;
-        float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+        // the accumulators start at -lse / -D, so the MMAs deliver S^T - lse and dP^T - D directly
+        const float2 ls = *reinterpret_cast<const float2*>(lsep + ib);
+        const float2 Dd = *reinterpret_cast<const float2*>(Dp + ib);
+        float s[4] = {-ls.x, -ls.y, -ls.x, -ls.y}, dp[4] = {-Dd.x, -Dd.y, -Dd.x, -Dd.y};
         {
           const uint32_t bq = QP[(ib + g) * LDC + 4 * h + t], bd = DP[(ib + g) * LDC + 4 * h + t];
           const uint32_t b0[2] = {bq, bq}, b1[2] = {bd, bd};
@@ -410,17 +413,12 @@ __device__ __forceinline__ void attn_core_bwd_single(const float* QPf, const flo
             if ((unsigned)(i - c0) < (unsigned)W && (unsigned)(j - c0) < (unsigned)W) s[e] += stab[(i - j + W - 1) * H + h];
           }
         }
-        const float2 ls = *reinterpret_cast<const float2*>(lsep + ib);
-        const float2 Dd = *reinterpret_cast<const float2*>(Dp + ib);
         float p[4], ds[4];
-        p[0] = fast_ex2(s[0] - ls.x);
-        p[1] = fast_ex2(s[1] - ls.y);
-        p[2] = fast_ex2(s[2] - ls.x);
-        p[3] = fast_ex2(s[3] - ls.y);
-        ds[0] = p[0] * (dp[0] - Dd.x);
-        ds[1] = p[1] * (dp[1] - Dd.y);
-        ds[2] = p[2] * (dp[2] - Dd.x);
-        ds[3] = p[3] * (dp[3] - Dd.y);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          p[e] = fast_ex2(s[e]);
+          ds[e] = p[e] * dp[e];
+        }
         if (cen && want_tab) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {

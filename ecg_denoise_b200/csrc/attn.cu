@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   __syncthreads();
 
   constexpr bool FW = (C <= RL_FW_MAXC);   // narrow stages: weight gradients are accumulated in-CTA (no wgrad launch)
-  if (FW) cta_wgrad<C, C, L>(sdq, LDC, sdk, LDC, a.d_wp, a.d_bp);          // dWp = g^T o,  dbp = sum g
+  if (FW) cta_wgrad_mma<C, C, L>(sdq, LDC, sdk, LDC, a.d_wp, a.d_bp, 0);          // dWp = g^T o,  dbp = sum g
   if (FW) __syncthreads();
   RL_TS(attn, 4);
 
@@ -300,9 +300,9 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   }
   RL_TS(attn, 9);
   if (FW) {   // dWq = dq^T u, dWkv = [dk | dv]^T u  (u now sits in su)
-    cta_wgrad<C, C, L>(sdq, LDC, su, LDC, a.d_wq, a.d_bq);
-    cta_wgrad<C, C, L>(sdk, LDC, su, LDC, a.d_wkv, a.d_bkv);
-    cta_wgrad<C, C, L>(sdv, LDC, su, LDC, a.d_wkv ? a.d_wkv + C * C : nullptr, a.d_bkv ? a.d_bkv + C : nullptr);
+    cta_wgrad_mma<C, C, L>(sdq, LDC, su, LDC, a.d_wq, a.d_bq, 0);
+    cta_wgrad_mma<C, C, L>(sdk, LDC, su, LDC, a.d_wkv, a.d_bkv, 5);
+    cta_wgrad_mma<C, C, L>(sdv, LDC, su, LDC, a.d_wkv ? a.d_wkv + C * C : nullptr, a.d_bkv ? a.d_bkv + C : nullptr, 10);
   }
   if (a.d_table && W > 0)
     for (int i = tid; i < (2 * W - 1) * H; i += RL_NT) atomicAdd(a.d_table + i, stabg[i]);

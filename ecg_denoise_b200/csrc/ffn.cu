@@ -322,8 +322,8 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
     __syncthreads();
   }
   if (FW) {   // dW2 = g^T g2, dW1 = dh^T u   (u now sits in su)
-    cta_wgrad<C, HC, L>(sg, LDC, sg2, LDH, a.d_w2, a.d_b2);
-    cta_wgrad<HC, C, L>(sd, LDH, su, LDC, a.d_w1, a.d_b1);
+    cta_wgrad_mma<C, HC, L>(sg, LDC, sg2, LDH, a.d_w2, a.d_b2, 0);
+    cta_wgrad_mma<HC, C, L>(sd, LDH, su, LDC, a.d_w1, a.d_b1, ((C + 15) / 16) * (HC / 8));
   }
 }
 

@@ -129,5 +129,11 @@ def call(fname: str, args: ctypes.Structure, stream: int):
     check(getattr(load(), fname)(ctypes.byref(args), ctypes.c_void_p(stream)))
 
 
+def set_attn_umma(on: bool) -> bool:
+    """select the forward kernels of the wide stages (C = 64, 128): True = tcgen05 tile kernels (attn_umma.cu),
+    False = one-window mma.sync kernels (attn.cu).  Same function either way; returns the previous setting."""
+    return bool(load().ralenet_set_attn_umma(1 if on else 0))
+
+
 def launch_count(reset: bool = False) -> int:
     return int(load().ralenet_launch_count(1 if reset else 0))

@@ -16,6 +16,9 @@
 
 RL_TRACE_DEFINE(attn)
 
+bool rl_attn_umma_enabled();                                            // tcgen05 forward kernels (attn_umma.cu)
+int rl_attn_fwd_umma(const rl_attn_fwd_args* a, cudaStream_t st);
+
 namespace {
 
 // weight streams: the wide stages pull their weights through deeper rings of smaller chunks (more loads in flight;
@@ -344,6 +347,10 @@ int launch_fwd(const rl_attn_fwd_args* a, cudaStream_t st) {
     if (int rc = rl_set_smem(attn_fwd_kernel<C, 2, 1>, smem)) return rc;
     rl_launch_pdl(attn_fwd_kernel<C, 2, 1>, dim3(a->B), dim3(RL_NT), smem, st, *a);
     return rl_check_launch("attn_fwd_kernel", C);
+  }
+  if (C >= 64 && rl_attn_umma_enabled()) {
+    const int rc = rl_attn_fwd_umma(a, st);                      // 1: shape not handled there
+    if (rc <= 0) return rc;
   }
   int done = 0;
   if (C >= 64 && a->B >= RL_NWC_MIN_B) {

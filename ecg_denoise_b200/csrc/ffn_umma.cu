@@ -37,21 +37,7 @@ struct FwdSmem {
   static constexpr size_t BYTES = sizeof(float) * (2 * A_FLOATS + 4 * B_FLOATS + 2 * TM) + 64;
 };
 
-// issue-side bookkeeping of the 2-deep weight ring: buffer b = chunk & 1 may be overwritten once the MMAs of the
-// chunk that used it two steps ago have completed (one commit per chunk on bar[b])
-struct Ring {
-  uint64_t* bar;
-  int chunk;
-  __device__ __forceinline__ int buf() const { return chunk & 1; }
-  __device__ __forceinline__ void wait_free() const {
-    if (chunk >= 2) umma::mbar_wait(bar + (chunk & 1), (uint32_t)(((chunk >> 1) - 1) & 1));
-  }
-  // wait until the MMAs of the most recently issued chunk (and everything before it) are complete
-  __device__ __forceinline__ void wait_last() const {
-    const int last = chunk - 1;
-    umma::mbar_wait(bar + (last & 1), (uint32_t)((last >> 1) & 1));
-  }
-};
+using umma::Ring;
 
 template <int C>
 __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_ffn_fwd_args a) {

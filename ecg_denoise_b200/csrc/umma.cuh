@@ -88,6 +88,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// issue-side bookkeeping of the 2-deep weight ring: buffer b = chunk & 1 may be overwritten once the MMAs of the
+// chunk that used it two steps ago have completed (one commit per chunk on bar[b])
+struct Ring {
+  uint64_t* bar;
+  int chunk;
+  __device__ __forceinline__ int buf() const { return chunk & 1; }
+  __device__ __forceinline__ void wait_free() const {
+    if (chunk >= 2) mbar_wait(bar + (chunk & 1), (uint32_t)(((chunk >> 1) - 1) & 1));
+  }
+  // wait until the MMAs of the most recently issued chunk (and everything before it) are complete
+  __device__ __forceinline__ void wait_last() const {
+    const int last = chunk - 1;
+    mbar_wait(bar + (last & 1), (uint32_t)((last >> 1) & 1));
+  }
+};
+
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

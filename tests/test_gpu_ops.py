@@ -142,6 +142,42 @@ def test_attn_fwd_paired_windows_bit_identical(ops, stage):
     assert torch.equal(xa.grad, xb.grad)
 
 
+@pytest.mark.parametrize("stage", [3, 4])
+@pytest.mark.parametrize("B", [3, 515])
+def test_attn_fwd_tile_kernels_match_one_window_kernels(ops, stage, B):
+    """Wide stages: the tcgen05 tile kernels (attn_umma.cu: 128 tokens = 4 / 8 windows per tile, heads split over a
+    cluster, partial last tile at both batch sizes) and the one-window mma.sync kernels (attn.cu) compute the same
+    function: outputs and the gradients driven by their saved q, k, v, o, lse agree far inside the tolerance."""
+    from ecg_denoise_b200 import _lib
+    rs = np.random.RandomState(500 + stage)
+    C, H, L = O.CHANNELS[stage], O.HEADS[stage], O.LENGTHS[stage]
+    p = _block_params(rs, C, 0)
+    W = O.RW_WINDOW[stage] if stage < 4 else 0
+    table = (0.5 * _rand(rs, 2 * W - 1, H)).float().cuda() if W else None
+    x = _rand(rs, B, L, C).float().cuda()
+    g = _rand(rs, B, L, C).float().cuda()
+    d = {k: v.float().cuda() for k, v in p.items()}
+    names = ("norm1.weight", "norm1.bias", "attn.qkv_proj.to_q.weight", "attn.qkv_proj.to_q.bias",
+             "attn.qkv_proj.to_kv.weight", "attn.qkv_proj.to_kv.bias", "attn.proj.weight", "attn.proj.bias")
+
+    def run(tile_kernels):
+        prev = _lib.set_attn_umma(tile_kernels)
+        try:
+            xs = x.clone().requires_grad_(True)
+            ps = [d[k].clone().requires_grad_(True) for k in names]
+            y = ops.AttnBlockFn.apply(xs, *ps, table, H, W, (L - W) // 2 if W else 0,
+                                      ops.RL_F_PRENORM | ops.RL_F_RESIDUAL)
+            y.backward(g)
+            torch.cuda.synchronize()
+            return [y.detach(), xs.grad] + [q.grad for q in ps]
+        finally:
+            _lib.set_attn_umma(prev)
+
+    a, b = run(True), run(False)
+    for name, ta, tb in zip(("y", "dx") + tuple("d_" + k for k in names), a, b):
+        _cmp(f"attn_tile_vs_window/s{stage}/B{B}/{name}", ta, tb, rtol=5e-5)
+
+
 def test_attn_plain_msattention(ops):
     """MSAttention.forward alone: no pre-norm, no residual (flags = 0)."""
     rs = np.random.RandomState(7)

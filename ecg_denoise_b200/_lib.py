@@ -129,10 +129,11 @@ def call(fname: str, args: ctypes.Structure, stream: int):
     check(getattr(load(), fname)(ctypes.byref(args), ctypes.c_void_p(stream)))
 
 
-def set_attn_umma(on: bool) -> bool:
-    """select the forward kernels of the wide stages (C = 64, 128): True = tcgen05 tile kernels (attn_umma.cu),
-    False = one-window mma.sync kernels (attn.cu).  Same function either way; returns the previous setting."""
-    return bool(load().ralenet_set_attn_umma(1 if on else 0))
+def set_attn_umma(mode: int) -> int:
+    """select the forward kernels of the wide stages (C = 64, 128): 2 = tcgen05 tile kernels (attn_umma.cu),
+    0 = one-window mma.sync kernels (attn.cu), 1 = tile kernels for single-wave launches only (default).
+    Same function either way; returns the previous mode."""
+    return int(load().ralenet_set_attn_umma(int(mode)))
 
 
 def launch_count(reset: bool = False) -> int:

@@ -16,8 +16,7 @@
 
 RL_TRACE_DEFINE(attn)
 
-bool rl_attn_umma_enabled();                                            // tcgen05 forward kernels (attn_umma.cu)
-int rl_attn_fwd_umma(const rl_attn_fwd_args* a, cudaStream_t st);
+int rl_attn_fwd_umma(const rl_attn_fwd_args* a, cudaStream_t st);       // tcgen05 tile kernels (attn_umma.cu)
 
 namespace {
 
@@ -348,8 +347,8 @@ int launch_fwd(const rl_attn_fwd_args* a, cudaStream_t st) {
     rl_launch_pdl(attn_fwd_kernel<C, 2, 1>, dim3(a->B), dim3(RL_NT), smem, st, *a);
     return rl_check_launch("attn_fwd_kernel", C);
   }
-  if (C >= 64 && rl_attn_umma_enabled()) {
-    const int rc = rl_attn_fwd_umma(a, st);                      // 1: shape not handled there
+  if (C >= 64) {
+    const int rc = rl_attn_fwd_umma(a, st);                      // 1: shape / batch not handled there
     if (rc <= 0) return rc;
   }
   int done = 0;

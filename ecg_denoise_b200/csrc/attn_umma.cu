@@ -28,7 +28,7 @@
 namespace cg = cooperative_groups;
 
 #ifndef RL_ATTN_UMMA_DEFAULT
-#define RL_ATTN_UMMA_DEFAULT 0   // off until the parity suite has run on a B200 with RALENET_ATTN_UMMA=1
+#define RL_ATTN_UMMA_DEFAULT 1   // see ralenet_set_attn_umma() below
 #endif
 
 RL_TRACE_DEFINE(attn_umma)
@@ -143,8 +143,10 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
     umma::fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc<TMEM_COLS>(tmem_slot);
-  if (W > 0)
-    for (int i = tid; i < (2 * W - 1) * H; i += RL_NT) stab[i] = __ldg(a.table + i) * RL_LOG2E;
+  // R-wave table ((2W-1) x H <= 128 entries, one per thread): the load is issued here and lands behind phase 1
+  const bool has_tab = W > 0 && tid < (2 * W - 1) * H;
+  float tabv = 0.f;
+  if (has_tab) tabv = __ldg(a.table + tid) * RL_LOG2E;
   RL_TS(attn_umma, 2);
 
   // 1. x*sqrt(C) + P -> LayerNorm -> A tile (K-major, KT = C) with its tf32 remainder     (transformer.py:386-387)
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
                                                           u.z - umma::trunc_tf32(u.z), u.w - umma::trunc_tf32(u.w));
     }
   }
+  if (has_tab) stab[tid] = tabv;
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
@@ -232,6 +235,19 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
   // the Wp slice of this CTA goes to registers now; its latency hides behind the epilogue and the attention core
   umma::KStage<C, CS, RL_NT> wpr;
   wpr.load(a.wp + CS * r, C, C);
+  // ... and so do the bias values of epilogue 1 (warp group w / 4 = 0, 1, 2 takes q, k, v)
+  float4 bias4[CS / 4];
+  {
+    const int seg = warp >> 2;
+    const float* bias = (seg == 0) ? a.bq : a.bkv;
+#pragma unroll
+    for (int i = 0; i < CS / 4; ++i) bias4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (seg < 3 && bias) {
+      bias += ((seg == 2) ? C : 0) + CS * r;
+#pragma unroll
+      for (int i = 0; i < CS / 4; ++i) bias4[i] = __ldg(reinterpret_cast<const float4*>(bias) + i);
+    }
+  }
   RL_TS(attn_umma, 4);
   ring.wait_last();
   umma::tc_fence_after();
@@ -251,14 +267,9 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
 #pragma unroll
         for (int i = 0; i < 16; ++i) { hv[i] = t0[i]; hv[16 + i] = t1[i]; }
       }
-      const float* bias = (seg == 0) ? a.bq : a.bkv;
-      if (bias) {
-        bias += ((seg == 2) ? C : 0) + CS * r;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + i));
-          hv[i] += b4.x; hv[i + 1] += b4.y; hv[i + 2] += b4.z; hv[i + 3] += b4.w;
-        }
+      for (int i = 0; i < CS / 4; ++i) {
+        hv[4 * i] += bias4[i].x; hv[4 * i + 1] += bias4[i].y; hv[4 * i + 2] += bias4[i].z; hv[4 * i + 3] += bias4[i].w;
       }
       float4* dst = reinterpret_cast<float4*>(r0 + seg * TM * LDS + row * LDS);
 #pragma unroll
@@ -277,16 +288,37 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
 
   // 3b. attention core of the HS heads of the NWT windows: one (window, head, 16-query tile) item per warp
   //     (attn_core.cuh); o overwrites q in place.  Windows attend only within themselves.
+  //     With 16 warps on the SM a warp interleaves TWO items (two independent MMA -> softmax -> MMA chains).
   {
     const int nwin = nvalid / L;
-    constexpr int NITEM = NWT * HS * QT;
+    constexpr int NITEM = NWT * HS * QT, NW = RL_NT / 32;
+    static_assert(NITEM % (2 * NW) == 0, "core: items are taken in pairs");
 #pragma unroll 1
-    for (int item = warp; item < NITEM; item += RL_NT / 32) {
-      const int w = item / (HS * QT), h = (item / QT) % HS, i0 = (item % QT) * 16;
-      if (w >= nwin) continue;
-      const int hg = HS * r + h;                              // head index within the layer
-      attn_core_fwd_item<L, LDS>(sq + w * L * LDS, sk + w * L * LDS, sv + w * L * LDS, 4 * h, i0, stab + hg, H, W, c0,
-                                 a.lse ? a.lse + ((size_t)(tile * NWT + w) * H + hg) * L : nullptr);
+    for (int base = warp; base < NITEM; base += 2 * NW) {
+      int w[2], hc[2], i0[2];
+      float* q2[2];
+      const float* k2[2];
+      const float* v2[2];
+      const float* t2[2];
+      float* l2[2];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int item = base + n * NW;
+        w[n] = item / (HS * QT);
+        const int h = (item / QT) % HS, hg = HS * r + h;      // head within the slice / within the layer
+        hc[n] = 4 * h;
+        i0[n] = (item % QT) * 16;
+        q2[n] = sq + w[n] * L * LDS;
+        k2[n] = sk + w[n] * L * LDS;
+        v2[n] = sv + w[n] * L * LDS;
+        t2[n] = stab + hg;
+        l2[n] = a.lse ? a.lse + ((size_t)(tile * NWT + w[n]) * H + hg) * L : nullptr;
+      }
+      if (w[0] >= nwin) continue;                             // items are ordered by window: w[1] >= w[0]
+      if (w[1] < nwin)
+        attn_core_fwd_items<L, LDS, 2>(q2, k2, v2, hc, i0, t2, H, W, c0, l2);
+      else
+        attn_core_fwd_item<L, LDS>(q2[0], k2[0], v2[0], hc[0], i0[0], t2[0], H, W, c0, l2[0]);
     }
   }
   __syncthreads();
@@ -340,17 +372,30 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
     }
   }
   umma::tc_fence_before();
+  // rows [r RPC, (r + 1) RPC) are finished here: their bias + residual terms are fetched before the cluster barrier
+  constexpr int RPC = TM / NSL, RIT = RPC * (C / 4) / RL_NT;  // rows finished by this CTA, float4 items per thread
+  static_assert(RPC * (C / 4) % RL_NT == 0, "reduce: items must tile the CTA");
+  float4 add4[RIT];
+#pragma unroll
+  for (int it = 0; it < RIT; ++it) {
+    const int i = tid + it * RL_NT;
+    const int rr = r * RPC + i / (C / 4), c = (i % (C / 4)) * 4;
+    add4[it] = a.bp ? __ldg(reinterpret_cast<const float4*>(a.bp + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((a.flags & RL_F_RESIDUAL) && rr < nvalid) {
+      const float4 x4 = __ldg(reinterpret_cast<const float4*>(a.x + (tok0 + rr) * C + c));
+      add4[it].x += x4.x; add4[it].y += x4.y; add4[it].z += x4.z; add4[it].w += x4.w;
+    }
+  }
   RL_TS(attn_umma, 9);
   cluster.sync();
   RL_TS(attn_umma, 10);
   {
-    constexpr int RPC = TM / NSL;                             // rows finished by this CTA
     const float* part[NSL];
 #pragma unroll
     for (int q = 0; q < NSL; ++q) part[q] = cluster.map_shared_rank(sp, q);
-    const float* bp = a.bp;
-    const bool resid = a.flags & RL_F_RESIDUAL;
-    for (int i = tid; i < RPC * (C / 4); i += RL_NT) {
+#pragma unroll
+    for (int it = 0; it < RIT; ++it) {
+      const int i = tid + it * RL_NT;
       const int rr = r * RPC + i / (C / 4), c = (i % (C / 4)) * 4;
       if (rr >= nvalid) continue;
       const int off = rr * LDP + c;
@@ -360,16 +405,8 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
         const float4 p = *reinterpret_cast<const float4*>(part[q] + off);
         s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
       }
-      if (bp) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(bp + c));
-        s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
-      }
-      const size_t g = (tok0 + rr) * C + c;
-      if (resid) {
-        const float4 x4 = __ldg(reinterpret_cast<const float4*>(a.x + g));
-        s.x += x4.x; s.y += x4.y; s.z += x4.z; s.w += x4.w;
-      }
-      *reinterpret_cast<float4*>(a.y + g) = s;
+      s.x += add4[it].x; s.y += add4[it].y; s.z += add4[it].z; s.w += add4[it].w;
+      *reinterpret_cast<float4*>(a.y + (tok0 + rr) * C + c) = s;
     }
   }
   RL_TS(attn_umma, 11);
@@ -405,27 +442,40 @@ int launch(const rl_attn_fwd_args& a, cudaStream_t st) {
 
 }  // namespace
 
-// Which forward kernels serve the wide stages: the tile kernels above (1) or the one-window mma.sync kernels of
-// attn.cu (0).  Initialised from RALENET_ATTN_UMMA (default RL_ATTN_UMMA_DEFAULT); ralenet_set_attn_umma() switches
-// it at run time for A/B measurements and the agreement test.  Both compute the same function.
+// Which forward kernels serve the wide stages: 0 = the one-window mma.sync kernels of attn.cu, 2 = the tile kernels
+// above, 1 (default) = the tile kernels while the launch is a single wave of CTAs (tiles * NSL <= SM count: the
+// training batch of 256 windows), the one-window / two-window kernels beyond (a tile CTA is a 20 us latency chain that
+// owns its SM, so throughput at large batches is better with two 16-warp CTAs per SM; measured 346 vs 276 us at
+// B = 4096, C = 128).  Initialised from RALENET_ATTN_UMMA; ralenet_set_attn_umma() switches it at run time for A/B
+// measurements and the agreement test.  All three compute the same function.
 static int g_attn_umma = -1;
-bool rl_attn_umma_enabled() {
+static int attn_umma_mode() {
   if (g_attn_umma < 0) {
     const char* e = getenv("RALENET_ATTN_UMMA");
-    g_attn_umma = (e && *e) ? (atoi(e) != 0) : RL_ATTN_UMMA_DEFAULT;
+    const int m = (e && *e) ? atoi(e) : RL_ATTN_UMMA_DEFAULT;
+    g_attn_umma = (m < 0 || m > 2) ? RL_ATTN_UMMA_DEFAULT : m;
   }
-  return g_attn_umma != 0;
+  return g_attn_umma;
 }
-extern "C" int ralenet_set_attn_umma(int on) {
-  const int prev = rl_attn_umma_enabled() ? 1 : 0;
-  g_attn_umma = on ? 1 : 0;
+extern "C" int ralenet_set_attn_umma(int mode) {
+  const int prev = attn_umma_mode();
+  g_attn_umma = (mode < 0 || mode > 2) ? RL_ATTN_UMMA_DEFAULT : mode;
   return prev;
 }
 
-// returns 1 if the shape is not handled here (caller falls through to attn_fwd_kernel)
+// returns 1 if the shape / batch is not handled here (caller falls through to attn_fwd_kernel)
 int rl_attn_fwd_umma(const rl_attn_fwd_args* a, cudaStream_t st) {
-  if (a->L * a->C != 2048) return 1;
-  if (a->C == 128) return launch<128>(*a, st);
-  if (a->C == 64) return launch<64>(*a, st);
-  return 1;
+  const int mode = attn_umma_mode();
+  if (mode == 0 || a->L * a->C != 2048 || (a->C != 64 && a->C != 128)) return 1;
+  if (mode == 1) {
+    static int n_sm = 0;
+    if (n_sm == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    }
+    const int ctas = (a->B * a->L + TM - 1) / TM * (a->C / CS);
+    if (ctas > n_sm) return 1;
+  }
+  return (a->C == 128) ? launch<128>(*a, st) : launch<64>(*a, st);
 }

@@ -98,11 +98,12 @@ typedef struct {
 
 int ralenet_attn_fwd(const rl_attn_fwd_args* a, void* stream);
 int ralenet_attn_bwd(const rl_attn_bwd_args* a, void* stream);
-/* Forward kernels of the wide stages (C = 64, 128): 1 = tcgen05 tile kernels (128 tokens = 4 / 8 windows per tile,
- * heads split over a cluster; attn_umma.cu), 0 = one-window mma.sync kernels (attn.cu).  Both compute the same
- * function; the switch exists for A/B measurements and the agreement test.  Initial value: environment variable
- * RALENET_ATTN_UMMA, else the build default.  Returns the previous setting.  Not thread-safe against running calls. */
-int ralenet_set_attn_umma(int on);
+/* Forward kernels of the wide stages (C = 64, 128).  mode 2: tcgen05 tile kernels (128 tokens = 4 / 8 windows per
+ * tile, heads split over a cluster; attn_umma.cu); mode 0: one-window mma.sync kernels (attn.cu); mode 1 (default):
+ * the tile kernels while the launch is a single wave of CTAs (the training batch), the others beyond.  All compute
+ * the same function; the switch exists for A/B measurements and the agreement test.  Initial value: environment
+ * variable RALENET_ATTN_UMMA.  Returns the previous mode.  Not thread-safe against running calls. */
+int ralenet_set_attn_umma(int mode);
 
 /* ------------------------------------------------------------------------------------------
  * Feed-forward half:  y = x + fc2(GELU(leconv(GELU(fc1(LN2(x))))))  (+ extra)

@@ -27,135 +27,98 @@ __device__ __forceinline__ uint32_t pack_hl(float x, bool sel_hi) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward, NI (head, 16-query tile) items at once: the calling warp streams the L keys of each item's window.
-// Item n: sq[n] / sk[n] / sv[n] = [L][LD] arrays of its window, the head's 4 channels at column hc[n], queries
-// i0[n] .. i0[n] + 15; o overwrites q in place.  stab_h[n]: R-wave table column of the head (element
-// (i - j + W - 1) at stab_h[n][(i - j + W - 1) * tab_stride]); lse_h[n]: [L] log-sum-exp row of the head (global,
-// log2 domain) or NULL.  NI = 2 interleaves two independent dependency chains (MMA -> max -> exp2 -> MMA) for the
-// callers that have only a few warps per scheduler (attn_umma.cu).
-template <int L, int LD, int NI>
-__device__ __forceinline__ void attn_core_fwd_items(float* const (&sq)[NI], const float* const (&sk)[NI],
-                                                    const float* const (&sv)[NI], const int (&hc)[NI],
-                                                    const int (&i0)[NI], const float* const (&stab_h)[NI],
-                                                    int tab_stride, int W, int c0, float* const (&lse_h)[NI]) {
-  constexpr int KT = L / 8, CH = (KT < 4) ? KT : 4;
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const float qs = 0.5f * RL_LOG2E;                  // head_dim^-0.5 (transformer.py:278) * log2(e)
-  const bool sel_hi = g < 4;
-  uint32_t qa[NI][4];
-  float m0[NI], m1[NI], l0[NI], l1[NI], o[NI][4];
-  bool qcen[NI];
-  const float* kp[NI];
-  const float* vp[NI];
-#pragma unroll
-  for (int n = 0; n < NI; ++n) {
-    const float* qp = sq[n] + (i0[n] + g) * LD + hc[n] + t;
-    split_tf32(qp[0] * qs, qa[n][0], qa[n][2]);
-    split_tf32(qp[8 * LD] * qs, qa[n][1], qa[n][3]);
-    m0[n] = m1[n] = -INFINITY;
-    l0[n] = l1[n] = 0.f;
-    o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-    qcen[n] = (W > 0) && (i0[n] + 16 > c0) && (i0[n] < c0 + W);
-    kp[n] = sk[n] + g * LD + hc[n] + t;
-    vp[n] = sv[n] + (2 * t) * LD + hc[n] + (g & 3);
-  }
-#pragma unroll 1
-  for (int j0 = 0; j0 < L; j0 += 8 * CH) {
-    float s[NI][CH][4];
-#pragma unroll
-    for (int n = 0; n < NI; ++n)
-#pragma unroll
-      for (int tt = 0; tt < CH; ++tt) {
-        uint32_t kh, kl;
-        split_tf32(kp[n][(j0 + 8 * tt) * LD], kh, kl);
-        s[n][tt][0] = s[n][tt][1] = s[n][tt][2] = s[n][tt][3] = 0.f;
-        const uint32_t bh[2] = {kh, kh}, bl[2] = {kl, kl};
-        mma_tf32(s[n][tt], qa[n], bh);
-        mma_tf32(s[n][tt], qa[n], bl);
-      }
-#pragma unroll
-    for (int n = 0; n < NI; ++n) {
-      if (qcen[n] && (j0 + 8 * CH > c0) && (j0 < c0 + W)) {        // R-wave bias on the central W x W block
-#pragma unroll
-        for (int tt = 0; tt < CH; ++tt)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = i0[n] + g + 8 * (e >> 1), j = j0 + 8 * tt + 2 * t + (e & 1);
-            if ((unsigned)(i - c0) < (unsigned)W && (unsigned)(j - c0) < (unsigned)W)
-              s[n][tt][e] += stab_h[n][(i - j + W - 1) * tab_stride];
-          }
-      }
-    }
-    float n0[NI], n1[NI];
-#pragma unroll
-    for (int n = 0; n < NI; ++n) {
-      float x0 = fmaxf(s[n][0][0], s[n][0][1]), x1 = fmaxf(s[n][0][2], s[n][0][3]);
-#pragma unroll
-      for (int tt = 1; tt < CH; ++tt) {
-        x0 = fmaxf(x0, fmaxf(s[n][tt][0], s[n][tt][1]));
-        x1 = fmaxf(x1, fmaxf(s[n][tt][2], s[n][tt][3]));
-      }
-      x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1));
-      x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1));
-      x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
-      x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
-      n0[n] = fmaxf(m0[n], x0);
-      n1[n] = fmaxf(m1[n], x1);
-      const float r0 = fast_ex2(m0[n] - n0[n]), r1 = fast_ex2(m1[n] - n1[n]);
-      l0[n] *= r0; l1[n] *= r1;
-      o[n][0] *= r0; o[n][1] *= r0; o[n][2] *= r1; o[n][3] *= r1;
-      m0[n] = n0[n]; m1[n] = n1[n];
-    }
-#pragma unroll
-    for (int tt = 0; tt < CH; ++tt)
-#pragma unroll
-      for (int n = 0; n < NI; ++n) {
-        const float p0 = fast_ex2(s[n][tt][0] - n0[n]), p1 = fast_ex2(s[n][tt][1] - n0[n]);
-        const float p2 = fast_ex2(s[n][tt][2] - n1[n]), p3 = fast_ex2(s[n][tt][3] - n1[n]);
-        l0[n] += p0 + p1;
-        l1[n] += p2 + p3;
-        uint32_t ah[4], al[4];
-        split_tf32(p0, ah[0], al[0]);
-        split_tf32(p2, ah[1], al[1]);
-        split_tf32(p1, ah[2], al[2]);
-        split_tf32(p3, ah[3], al[3]);
-        const float* vq = vp[n] + (j0 + 8 * tt) * LD;
-        const uint32_t b[2] = {pack_hl(vq[0], sel_hi), pack_hl(vq[LD], sel_hi)};
-        mma_tf32(o[n], ah, b);
-        mma_tf32(o[n], al, b);
-      }
-  }
-#pragma unroll
-  for (int n = 0; n < NI; ++n) {
-    l0[n] += __shfl_xor_sync(0xffffffffu, l0[n], 1);
-    l1[n] += __shfl_xor_sync(0xffffffffu, l1[n], 1);
-    l0[n] += __shfl_xor_sync(0xffffffffu, l0[n], 2);
-    l1[n] += __shfl_xor_sync(0xffffffffu, l1[n], 2);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) o[n][e] += __shfl_xor_sync(0xffffffffu, o[n][e], 2);     // hi columns + lo columns
-    if (t < 2) {
-      const float v0 = 1.0f / l0[n], v1 = 1.0f / l1[n];
-      *reinterpret_cast<float2*>(sq[n] + (i0[n] + g) * LD + hc[n] + 2 * t) = make_float2(o[n][0] * v0, o[n][1] * v0);
-      *reinterpret_cast<float2*>(sq[n] + (i0[n] + g + 8) * LD + hc[n] + 2 * t) = make_float2(o[n][2] * v1, o[n][3] * v1);
-    }
-    if (lse_h[n] != nullptr && t == 0) {
-      lse_h[n][i0[n] + g] = m0[n] + log2f(l0[n]);
-      lse_h[n][i0[n] + g + 8] = m1[n] + log2f(l1[n]);
-    }
-  }
-}
-
+// forward, one (head, 16-query tile) item of one window: the calling warp streams the L keys of the window.
+// sq / sk / sv: [L][LD] arrays of the window, the head's 4 channels at column hc; o overwrites q in place.
+// stab_h: R-wave table column of this head (element (i - j + W - 1) at stab_h[(i - j + W - 1) * tab_stride]);
+// lse_h: [L] log-sum-exp row of this head (global, log2 domain) or NULL.
 template <int L, int LD>
 __device__ __forceinline__ void attn_core_fwd_item(float* sq, const float* sk, const float* sv, int hc, int i0,
                                                    const float* stab_h, int tab_stride, int W, int c0,
                                                    float* __restrict__ lse_h) {
-  float* const q1[1] = {sq};
-  const float* const k1[1] = {sk};
-  const float* const v1[1] = {sv};
-  const int h1[1] = {hc}, i1[1] = {i0};
-  const float* const t1[1] = {stab_h};
-  float* const l1[1] = {lse_h};
-  attn_core_fwd_items<L, LD, 1>(q1, k1, v1, h1, i1, t1, tab_stride, W, c0, l1);
+  constexpr int KT = L / 8, CH = (KT < 4) ? KT : 4;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const float qs = 0.5f * RL_LOG2E;                  // head_dim^-0.5 (transformer.py:278) * log2(e)
+  const bool sel_hi = g < 4;
+  uint32_t qa[4];
+  {
+    const float* qp = sq + (i0 + g) * LD + hc + t;
+    split_tf32(qp[0] * qs, qa[0], qa[2]);
+    split_tf32(qp[8 * LD] * qs, qa[1], qa[3]);
+  }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool qcen = (W > 0) && (i0 + 16 > c0) && (i0 < c0 + W);
+  const float* kp = sk + g * LD + hc + t;
+  const float* vp = sv + (2 * t) * LD + hc + (g & 3);
+#pragma unroll 1
+  for (int j0 = 0; j0 < L; j0 += 8 * CH) {
+    float s[CH][4];
+#pragma unroll
+    for (int tt = 0; tt < CH; ++tt) {
+      uint32_t kh, kl;
+      split_tf32(kp[(j0 + 8 * tt) * LD], kh, kl);
+      s[tt][0] = s[tt][1] = s[tt][2] = s[tt][3] = 0.f;
+      const uint32_t bh[2] = {kh, kh}, bl[2] = {kl, kl};
+      mma_tf32(s[tt], qa, bh);
+      mma_tf32(s[tt], qa, bl);
+    }
+    if (qcen && (j0 + 8 * CH > c0) && (j0 < c0 + W)) {        // R-wave bias on the central W x W block
+#pragma unroll
+      for (int tt = 0; tt < CH; ++tt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = i0 + g + 8 * (e >> 1), j = j0 + 8 * tt + 2 * t + (e & 1);
+          if ((unsigned)(i - c0) < (unsigned)W && (unsigned)(j - c0) < (unsigned)W)
+            s[tt][e] += stab_h[(i - j + W - 1) * tab_stride];
+        }
+    }
+    float x0 = fmaxf(s[0][0], s[0][1]), x1 = fmaxf(s[0][2], s[0][3]);
+#pragma unroll
+    for (int tt = 1; tt < CH; ++tt) {
+      x0 = fmaxf(x0, fmaxf(s[tt][0], s[tt][1]));
+      x1 = fmaxf(x1, fmaxf(s[tt][2], s[tt][3]));
+    }
+    x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1));
+    x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1));
+    x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
+    x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
+    const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);
+    const float r0 = fast_ex2(m0 - n0), r1 = fast_ex2(m1 - n1);
+    l0 *= r0; l1 *= r1;
+    o[0] *= r0; o[1] *= r0; o[2] *= r1; o[3] *= r1;
+    m0 = n0; m1 = n1;
+#pragma unroll
+    for (int tt = 0; tt < CH; ++tt) {
+      const float p0 = fast_ex2(s[tt][0] - n0), p1 = fast_ex2(s[tt][1] - n0);
+      const float p2 = fast_ex2(s[tt][2] - n1), p3 = fast_ex2(s[tt][3] - n1);
+      l0 += p0 + p1;
+      l1 += p2 + p3;
+      uint32_t ah[4], al[4];
+      split_tf32(p0, ah[0], al[0]);
+      split_tf32(p2, ah[1], al[1]);
+      split_tf32(p1, ah[2], al[2]);
+      split_tf32(p3, ah[3], al[3]);
+      const float* vq = vp + (j0 + 8 * tt) * LD;
+      const uint32_t b[2] = {pack_hl(vq[0], sel_hi), pack_hl(vq[LD], sel_hi)};
+      mma_tf32(o, ah, b);
+      mma_tf32(o, al, b);
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) o[e] += __shfl_xor_sync(0xffffffffu, o[e], 2);     // hi columns + lo columns
+  if (t < 2) {
+    const float v0 = 1.0f / l0, v1 = 1.0f / l1;
+    *reinterpret_cast<float2*>(sq + (i0 + g) * LD + hc + 2 * t) = make_float2(o[0] * v0, o[1] * v0);
+    *reinterpret_cast<float2*>(sq + (i0 + g + 8) * LD + hc + 2 * t) = make_float2(o[2] * v1, o[3] * v1);
+  }
+  if (lse_h != nullptr && t == 0) {
+    lse_h[i0 + g] = m0 + log2f(l0);
+    lse_h[i0 + g + 8] = m1 + log2f(l1);
+  }
 }
 
 // forward over one window held as [L][ld_mk(C)] arrays: one warp per (head, 16-query tile) item.

@@ -288,37 +288,16 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
 
   // 3b. attention core of the HS heads of the NWT windows: one (window, head, 16-query tile) item per warp
   //     (attn_core.cuh); o overwrites q in place.  Windows attend only within themselves.
-  //     With 16 warps on the SM a warp interleaves TWO items (two independent MMA -> softmax -> MMA chains).
   {
     const int nwin = nvalid / L;
-    constexpr int NITEM = NWT * HS * QT, NW = RL_NT / 32;
-    static_assert(NITEM % (2 * NW) == 0, "core: items are taken in pairs");
+    constexpr int NITEM = NWT * HS * QT;
 #pragma unroll 1
-    for (int base = warp; base < NITEM; base += 2 * NW) {
-      int w[2], hc[2], i0[2];
-      float* q2[2];
-      const float* k2[2];
-      const float* v2[2];
-      const float* t2[2];
-      float* l2[2];
-#pragma unroll
-      for (int n = 0; n < 2; ++n) {
-        const int item = base + n * NW;
-        w[n] = item / (HS * QT);
-        const int h = (item / QT) % HS, hg = HS * r + h;      // head within the slice / within the layer
-        hc[n] = 4 * h;
-        i0[n] = (item % QT) * 16;
-        q2[n] = sq + w[n] * L * LDS;
-        k2[n] = sk + w[n] * L * LDS;
-        v2[n] = sv + w[n] * L * LDS;
-        t2[n] = stab + hg;
-        l2[n] = a.lse ? a.lse + ((size_t)(tile * NWT + w[n]) * H + hg) * L : nullptr;
-      }
-      if (w[0] >= nwin) continue;                             // items are ordered by window: w[1] >= w[0]
-      if (w[1] < nwin)
-        attn_core_fwd_items<L, LDS, 2>(q2, k2, v2, hc, i0, t2, H, W, c0, l2);
-      else
-        attn_core_fwd_item<L, LDS>(q2[0], k2[0], v2[0], hc[0], i0[0], t2[0], H, W, c0, l2[0]);
+    for (int item = warp; item < NITEM; item += RL_NT / 32) {
+      const int w = item / (HS * QT), h = (item / QT) % HS, i0 = (item % QT) * 16;
+      if (w >= nwin) continue;
+      const int hg = HS * r + h;                              // head index within the layer
+      attn_core_fwd_item<L, LDS>(sq + w * L * LDS, sk + w * L * LDS, sv + w * L * LDS, 4 * h, i0, stab + hg, H, W, c0,
+                                 a.lse ? a.lse + ((size_t)(tile * NWT + w) * H + hg) * L : nullptr);
     }
   }
   __syncthreads();

@@ -206,6 +206,9 @@ __device__ __forceinline__ void ln_forward_rows(int rows, Load load, Store store
   using G = LnGeom<C>;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gl = lane % G::GS, gi = lane / G::GS;
+  // unrolled (rows is a compile-time constant at the call sites: 1 - 8 trips) so that the global loads of every trip
+  // are in flight together instead of one L2 round trip per trip
+#pragma unroll
   for (int t0 = 0; t0 < rows; t0 += G::TPI) {
     const int t = t0 + warp * G::TPW + gi;
     const bool ok = t < rows;
@@ -248,6 +251,7 @@ __device__ __forceinline__ void ln_backward_rows(int rows, const float* __restri
     ag[i] = 0.f;
     ab[i] = 0.f;
   }
+#pragma unroll
   for (int t0 = 0; t0 < rows; t0 += G::TPI) {
     const int t = t0 + warp * G::TPW + gi;
     const bool ok = t < rows;

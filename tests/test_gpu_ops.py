@@ -103,10 +103,22 @@ def test_attn_block(ops, stage, bias):
 
 
 @pytest.mark.parametrize("stage", [3, 4])
-def test_attn_fwd_paired_windows_bit_identical(ops, stage):
-    """At the wide stages large batches put two windows on a CTA (attn.cu, NWC) and the odd last windows go
-    through the one-window kernel: outputs and every saved tensor must equal, bit for bit, what the one-window
-    kernel gives on the same windows in small batches (no window may see its CTA neighbour)."""
+@pytest.mark.parametrize("mode", [0, 2])
+def test_attn_fwd_paired_windows_bit_identical(ops, stage, mode):
+    """At the wide stages several windows share a CTA.  mode 0 (attn.cu): large batches put two windows on a CTA and
+    the odd last windows go through the one-window kernel; mode 2 (attn_umma.cu): 4 / 8 windows form a 128-token
+    tile, the last tile partial.  Outputs and every saved tensor must equal, bit for bit, what the same kernels give
+    on the same windows in small batches, where they sit at other positions of their CTA / tile (no window may see
+    its neighbours)."""
+    from ecg_denoise_b200 import _lib
+    prev = _lib.set_attn_umma(mode)
+    try:
+        _paired_windows_bit_identical(ops, stage)
+    finally:
+        _lib.set_attn_umma(prev)
+
+
+def _paired_windows_bit_identical(ops, stage):
     rs = np.random.RandomState(300 + stage)
     C, H, L = O.CHANNELS[stage], O.HEADS[stage], O.LENGTHS[stage]
     B = 515                                # 257 two-window CTAs + one odd window

@@ -49,7 +49,10 @@ struct ASmem {
   static constexpr int R0 = cmax(cmax(2 * TM * C, 3 * TM * LDS), TM * (C + 4));
   // region 1: weight ring of the q|k|v GEMM (2 stages x (hi | lo)) -> o tile (hi | lo) + Wp slice (hi | lo)
   static constexpr int R1 = cmax(4 * NQ * KC, 2 * TM * CS + 2 * C * CS);
-  static constexpr size_t BYTES = sizeof(float) * (R0 + R1 + 128) + 64;
+  // constants staged before the dependency wait: positional tile [L][C + 4] (L * C = 2048), norm1 weight | bias
+  static constexpr int LDPE = C + 4;
+  static constexpr int CONSTS = (2048 / C) * LDPE + 2 * C;
+  static constexpr size_t BYTES = sizeof(float) * (R0 + R1 + 128 + CONSTS) + 64;
 };
 
 // Staging of one K chunk of the [q | k | v] weight rows of head slice r into a K-major tile pair:
@@ -107,16 +110,33 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
 #pragma unroll
     for (int j = 0; j < NCHK; ++j) wr[j].load(a.wq, a.wkv, rp, C, j * KC);
   }
-  RL_TS(attn_umma, 0);
-  pdl_wait();
-  pdl_trigger();
-  RL_TS(attn_umma, 1);
   extern __shared__ __align__(128) float smem[];
   float* r0 = smem;
   float* r1 = smem + ASmem<C>::R0;
   float* stab = r1 + ASmem<C>::R1;                           // R-wave table * log2(e), (2W-1) x H <= 128 floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stab + 128);  // 2 mbarriers
+  float* s_pe = stab + 128;                                  // positional tile [L][LDPE]
+  float* s_ln = s_pe + L * ASmem<C>::LDPE;                   // norm1 weight [C] | bias [C]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ln + 2 * C);   // 2 mbarriers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  // ... and so do the constants of phase 1 (positional tile, LayerNorm affine) and the R-wave table: staged in
+  // shared memory here, phase 1 then waits for ONE round of global loads (x) instead of three
+  {
+    constexpr int LDPE = ASmem<C>::LDPE;
+    const int t = threadIdx.x;
+    if (a.flags & RL_F_PRENORM) {
+      static_assert(L * C / 4 == RL_NT, "one float4 of the positional tile per thread");
+      const float4 p4 = __ldg(reinterpret_cast<const float4*>(a.pe) + t);
+      float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < C / 2) l4 = __ldg(reinterpret_cast<const float4*>(t < C / 4 ? a.ln_w : a.ln_b) + (t % (C / 4)));
+      *reinterpret_cast<float4*>(s_pe + (t / (C / 4)) * LDPE + 4 * (t % (C / 4))) = p4;
+      if (t < C / 2) *reinterpret_cast<float4*>(s_ln + 4 * t) = l4;
+    }
+    if (a.W > 0 && t < (2 * a.W - 1) * H) stab[t] = __ldg(a.table + t) * RL_LOG2E;   // (2W-1) x H <= 128 entries
+  }
+  RL_TS(attn_umma, 0);
+  pdl_wait();
+  pdl_trigger();
+  RL_TS(attn_umma, 1);
   float* sA_hi = r0;                                         // u tile, K-major, KT = C
   float* sA_lo = r0 + TM * C;
   float* sq = r0;                                            // q, k, v slices [TM][LDS] (over the dead u tile)
@@ -143,10 +163,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
     umma::fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc<TMEM_COLS>(tmem_slot);
-  // R-wave table ((2W-1) x H <= 128 entries, one per thread): the load is issued here and lands behind phase 1
-  const bool has_tab = W > 0 && tid < (2 * W - 1) * H;
-  float tabv = 0.f;
-  if (has_tab) tabv = __ldg(a.table + tid) * RL_LOG2E;
+  __syncthreads();                                           // staged constants visible to every warp
   RL_TS(attn_umma, 2);
 
   // 1. x*sqrt(C) + P -> LayerNorm -> A tile (K-major, KT = C) with its tf32 remainder     (transformer.py:386-387)
@@ -165,7 +182,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
       const int qc = qsub + 4 * i;
       v[i] = ok ? __ldg(reinterpret_cast<const float4*>(xw + (size_t)row * C) + qc) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (pre) {
-        const float4 p4 = __ldg(reinterpret_cast<const float4*>(a.pe + (size_t)(row % L) * C) + qc);
+        const float4 p4 = *reinterpret_cast<const float4*>(s_pe + (row % L) * ASmem<C>::LDPE + 4 * qc);
         v[i].x = fmaf(v[i].x, sc, p4.x); v[i].y = fmaf(v[i].y, sc, p4.y);
         v[i].z = fmaf(v[i].z, sc, p4.z); v[i].w = fmaf(v[i].w, sc, p4.w);
       }
@@ -191,8 +208,8 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
       const int qc = qsub + 4 * i;
       float4 u = v[i];
       if (pre) {
-        const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.ln_w) + qc);
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b) + qc);
+        const float4 w4 = *reinterpret_cast<const float4*>(s_ln + 4 * qc);
+        const float4 b4 = *reinterpret_cast<const float4*>(s_ln + C + 4 * qc);
         u.x = fmaf((v[i].x - mu) * rstd, w4.x, b4.x);
         u.y = fmaf((v[i].y - mu) * rstd, w4.y, b4.y);
         u.z = fmaf((v[i].z - mu) * rstd, w4.z, b4.z);
@@ -205,7 +222,6 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
                                                           u.z - umma::trunc_tf32(u.z), u.w - umma::trunc_tf32(u.w));
     }
   }
-  if (has_tab) stab[tid] = tabv;
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
@@ -274,16 +290,25 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
       float4* dst = reinterpret_cast<float4*>(r0 + seg * TM * LDS + row * LDS);
 #pragma unroll
       for (int i = 0; i < 8; ++i) dst[i] = make_float4(hv[4 * i], hv[4 * i + 1], hv[4 * i + 2], hv[4 * i + 3]);
-      float* gsave = (seg == 0) ? a.q : (seg == 1) ? a.k : a.v;
-      if (gsave && row < nvalid) {
-        float4* gs = reinterpret_cast<float4*>(gsave + (tok0 + row) * C + CS * r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) gs[i] = make_float4(hv[4 * i], hv[4 * i + 1], hv[4 * i + 2], hv[4 * i + 3]);
-      }
     }
   }
   umma::tc_fence_before();     // the tcgen05.ld reads of the q|k|v accumulator precede the barrier below
   __syncthreads();
+  // q, k, v slices -> global memory for the backward: 8 lanes cover the 128 contiguous bytes of one token, so a warp
+  // writes four full lines per store (one thread per row, as the accumulator is read, would touch 32 lines)
+  if (a.q) {
+#pragma unroll
+    for (int it = 0; it < 3 * TM * (CS / 4) / RL_NT; ++it) {
+      const int idx = tid + it * RL_NT;
+      const int seg = idx / (TM * (CS / 4)), row = (idx / (CS / 4)) % TM, c4 = idx % (CS / 4);
+      if (row < nvalid) {
+        float* gsave = (seg == 0) ? a.q : (seg == 1) ? a.k : a.v;
+        *reinterpret_cast<float4*>(gsave + (tok0 + row) * C + CS * r + 4 * c4) =
+            *reinterpret_cast<const float4*>(r0 + seg * TM * LDS + row * LDS + 4 * c4);
+      }
+    }
+    __syncthreads();           // q is overwritten by o below
+  }
   RL_TS(attn_umma, 6);
 
   // 3b. attention core of the HS heads of the NWT windows: one (window, head, 16-query tile) item per warp

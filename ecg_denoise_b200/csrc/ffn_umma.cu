@@ -34,7 +34,7 @@ template <int C>
 struct FwdSmem {
   static constexpr int A_FLOATS = TM * TS;             // u tile [TM][C] and later the g2 tile [TM][TS] (C <= TS)
   static constexpr int B_FLOATS = 128 * KC;            // one weight chunk (up to 128 rows)
-  static constexpr size_t BYTES = sizeof(float) * (2 * A_FLOATS + 4 * B_FLOATS + 2 * TM) + 64;
+  static constexpr size_t BYTES = sizeof(float) * (2 * A_FLOATS + 4 * B_FLOATS + 2 * TM + 2 * C) + 64;
 };
 
 using umma::Ring;
@@ -50,18 +50,26 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
 #pragma unroll
     for (int j = 0; j < C / KC; ++j) w1r[j].load(w1s + j * KC, C, TS);
   }
-  RL_TS(umma, 0);
-  pdl_wait();
-  pdl_trigger();
-  RL_TS(umma, 1);
   extern __shared__ __align__(128) float smem[];
   float* sA_hi = smem;
   float* sA_lo = sA_hi + FwdSmem<C>::A_FLOATS;
   float* sB = sA_lo + FwdSmem<C>::A_FLOATS;                  // [2 stages][hi | lo][128 * KC]
   float* sg10 = sB + 4 * FwdSmem<C>::B_FLOATS;               // g1[:, 0] of the tile (slice 0)
   float* sfir = sg10 + TM;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sfir + TM);   // 2 mbarriers
+  float* s_ln = sfir + TM;                                   // norm2 weight [C] | bias [C]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ln + 2 * C);   // 2 mbarriers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  // ... and so does the LayerNorm affine: staged in shared memory here, phase 1 then waits for one round of global
+  // loads (x) instead of one more round per 16-byte chunk
+  if ((a.flags & RL_F_PRENORM) && threadIdx.x < C / 2) {
+    const int t = threadIdx.x;
+    *reinterpret_cast<float4*>(s_ln + 4 * t) =
+        __ldg(reinterpret_cast<const float4*>(t < C / 4 ? a.ln_w : a.ln_b) + (t % (C / 4)));
+  }
+  RL_TS(umma, 0);
+  pdl_wait();
+  pdl_trigger();
+  RL_TS(umma, 1);
 
   cg::cluster_group cluster = cg::this_cluster();
   const int r = (int)cluster.block_rank();
@@ -77,6 +85,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
     umma::fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc<TMEM_COLS>(tmem_slot);
+  __syncthreads();                                           // staged LayerNorm affine visible to every warp
   RL_TS(umma, 2);
 
   // 1. LN2 over the TM tokens -> A tile (K-major, KT = C) with its tf32 remainder.  A warp owns 8 rows; lane =
@@ -114,8 +123,8 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
       const int qc = qsub + 4 * i;
       float4 u = v[i];
       if (a.flags & RL_F_PRENORM) {
-        const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.ln_w) + qc);
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b) + qc);
+        const float4 w4 = *reinterpret_cast<const float4*>(s_ln + 4 * qc);
+        const float4 b4 = *reinterpret_cast<const float4*>(s_ln + C + 4 * qc);
         u.x = fmaf((v[i].x - mu) * rstd, w4.x, b4.x);
         u.y = fmaf((v[i].y - mu) * rstd, w4.y, b4.y);
         u.z = fmaf((v[i].z - mu) * rstd, w4.z, b4.z);

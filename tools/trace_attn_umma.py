@@ -11,6 +11,7 @@ from ecg_denoise_b200.ops import pos_table
 
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+SAVE = int(sys.argv[3]) if len(sys.argv) > 3 else 1          # 0: inference mode (no q, k, v, o, lse saves)
 L, H = 2048 // C, C // 4
 W = 4 if C == 64 else 0
 dev = torch.device("cuda:0")
@@ -27,8 +28,11 @@ y, q, k, v, o = (torch.empty_like(x) for _ in range(5))
 lse = torch.empty(B, H, L, device=dev)
 A.B, A.L, A.C, A.H, A.W, A.c0, A.flags = B, L, C, H, W, (L - W) // 2 if W else 0, 3
 for name, t in dict(x=x, pe=pe, ln_w=p["ln_w"], ln_b=p["ln_b"], wq=p["wq"], bq=p["bq"], wkv=p["wkv"], bkv=p["bkv"],
-                    wp=p["wp"], bp=p["bp"], y=y, q=q, k=k, v=v, o=o, lse=lse).items():
+                    wp=p["wp"], bp=p["bp"], y=y).items():
     setattr(A, name, t.data_ptr())
+if SAVE:
+    for name, t in dict(q=q, k=k, v=v, o=o, lse=lse).items():
+        setattr(A, name, t.data_ptr())
 if W:
     A.table = p["table"].data_ptr()
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -49,9 +53,9 @@ def timed(n=20):
 
 
 _lib.set_attn_umma(0)
-print(f"C={C} B={B}: one-window mma.sync kernel {timed():.2f} us per launch (back to back)")
+print(f"C={C} B={B} save={SAVE}: one-window mma.sync kernel {timed():.2f} us per launch (back to back)")
 _lib.set_attn_umma(2)
-print(f"C={C} B={B}: tcgen05 tile kernel       {timed():.2f} us per launch (back to back)")
+print(f"C={C} B={B} save={SAVE}: tcgen05 tile kernel       {timed():.2f} us per launch (back to back)")
 if not hasattr(lib, "ralenet_debug_trace_read_attn_umma"):
     sys.exit(0)
 ncta = ((B * L + 127) // 128) * (C // 32)

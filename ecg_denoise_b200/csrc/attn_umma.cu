@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
       }
       s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
+    RL_TS(attn_umma, 13);                                     // (trace) the x loads have landed
     float mu = 0.f, rstd = 1.f;
     if (pre) {
       s += __shfl_xor_sync(0xffffffffu, s, 8);
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
       q += __shfl_xor_sync(0xffffffffu, q, 16);
       rstd = rsqrtf(q * (1.0f / C) + RL_LN_EPS);
     }
+    RL_TS(attn_umma, 14);                                     // (trace) statistics done
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
       const int qc = qsub + 4 * i;

@@ -703,4 +703,7 @@ bool rl_attn_bwd_has_wgrad(const rl_attn_bwd_args* a);
 int rl_ffn_bwd_main(const rl_ffn_bwd_args* a, cudaStream_t st);
 int rl_ffn_bwd_wgrad(const rl_ffn_bwd_args* a, cudaStream_t st);
 bool rl_ffn_bwd_has_wgrad(const rl_ffn_bwd_args* a);
+int rl_patch_bwd_main(const rl_patch_bwd_args* a, cudaStream_t st);
+int rl_patch_bwd_wgrad(const rl_patch_bwd_args* a, cudaStream_t st);
+bool rl_patch_bwd_has_wgrad(const rl_patch_bwd_args* a);
 bool rl_prof_active();                 // per-launch profiling is on: keep every launch on the profiled stream

@@ -261,6 +261,9 @@ extern "C" int ralenet_net_bwd(const rl_net_cfg* cfg, const rl_net_ptrs* P, cons
   // fork the weight gradients of main kernel n; `launch` enqueues them on the given stream
   auto fork_wgrad = [&](bool has, auto launch) -> int {
     if (!has) return RL_OK;
+#ifdef RL_DEBUG_SKIP_WGRAD     // timing experiment only (wrong gradients): what do the side-stream GEMMs cost the main chain?
+    return RL_OK;
+#endif
     if (!use_side) return launch(st_main);
     const int slot = n & 3;
     cudaEventRecord(sc->ev_main[slot], st_main);
@@ -289,7 +292,9 @@ extern "C" int ralenet_net_bwd(const rl_net_cfg* cfg, const rl_net_ptrs* P, cons
         before_main();
         pa.dx = rot(); pa.gsum = nullptr;
         pa.d_w = G->ps[j][0]; pa.d_ln_w = G->ps[j][1]; pa.d_ln_b = G->ps[j][2];
-        if ((rc = ralenet_patch_bwd(&pa, stream))) return rc;
+        if ((rc = rl_patch_bwd_main(&pa, st_main))) return rc;
+        if ((rc = fork_wgrad(rl_patch_bwd_has_wgrad(&pa), [&](cudaStream_t q) { return rl_patch_bwd_wgrad(&pa, q); })))
+          return rc;
         ++n;
         g = pa.dx;
       } else if (layer < 4) {
@@ -301,7 +306,9 @@ extern "C" int ralenet_net_bwd(const rl_net_cfg* cfg, const rl_net_ptrs* P, cons
         before_main();
         pa.dx = rot(); pa.gsum = w.gsum;
         pa.d_w = G->pm[layer][0]; pa.d_ln_w = G->pm[layer][1]; pa.d_ln_b = G->pm[layer][2];
-        if ((rc = ralenet_patch_bwd(&pa, stream))) return rc;
+        if ((rc = rl_patch_bwd_main(&pa, st_main))) return rc;
+        if ((rc = fork_wgrad(rl_patch_bwd_has_wgrad(&pa), [&](cudaStream_t q) { return rl_patch_bwd_wgrad(&pa, q); })))
+          return rc;
         ++n;
         g = pa.dx;
       }

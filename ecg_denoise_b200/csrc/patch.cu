@@ -166,24 +166,36 @@ extern "C" int ralenet_patch_fwd(const rl_patch_fwd_args* a, void* stream) {
 }
 
 // gsum: scratch [B, L*C] holding g + g2 when g2 is given (dx is used for it: see below)
-extern "C" int ralenet_patch_bwd(const rl_patch_bwd_args* a, void* stream) {
+// the data-gradient kernel (also leaves g + g2 in gsum for the weight gradient)
+int rl_patch_bwd_main(const rl_patch_bwd_args* a, cudaStream_t st) {
   RL_REQUIRE(a, RL_ERR_NULL, "patch_bwd: args is NULL");
   int CN = 0;
   if (int rc = check_shape(a->B, a->L, a->C, a->mode, &CN)) return rc;
   RL_REQUIRE(a->g && a->x && a->w && a->ln_w && a->u && a->dx, RL_ERR_NULL, "patch_bwd: NULL tensor");
   RL_REQUIRE(!a->d_ln_w == !a->d_ln_b, RL_ERR_NULL, "patch_bwd: d_ln_w/d_ln_b must be both set or both NULL");
   RL_REQUIRE(!a->g2 || a->gsum, RL_ERR_NULL, "patch_bwd: g2 needs the gsum scratch");
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc = RL_ERR_SHAPE;
   switch (CN) {
-    case 8: rc = launch_bwd<8>(a, a->gsum, st); break;
-    case 16: rc = launch_bwd<16>(a, a->gsum, st); break;
-    case 32: rc = launch_bwd<32>(a, a->gsum, st); break;
-    case 64: rc = launch_bwd<64>(a, a->gsum, st); break;
-    case 128: rc = launch_bwd<128>(a, a->gsum, st); break;
+    case 8: return launch_bwd<8>(a, a->gsum, st);
+    case 16: return launch_bwd<16>(a, a->gsum, st);
+    case 32: return launch_bwd<32>(a, a->gsum, st);
+    case 64: return launch_bwd<64>(a, a->gsum, st);
+    case 128: return launch_bwd<128>(a, a->gsum, st);
   }
-  if (rc) return rc;
+  return RL_ERR_SHAPE;
+}
+
+bool rl_patch_bwd_has_wgrad(const rl_patch_bwd_args* a) { return a->d_w != nullptr; }
+
+// dW = (g + g2)^T u over all tokens; may run on another stream once the main kernel is done
+int rl_patch_bwd_wgrad(const rl_patch_bwd_args* a, cudaStream_t st) {
+  const int CN = (a->mode == 0) ? 2 * a->C : a->C / 2;
   const int M = a->B * (a->L * a->C / CN);
   const RlWgradDesc d[1] = {{a->g2 ? a->gsum : a->g, CN, a->u, CN, CN, CN, a->d_w, nullptr}};
   return rl_launch_wgrad_group(d, 1, M, st);
+}
+
+extern "C" int ralenet_patch_bwd(const rl_patch_bwd_args* a, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = rl_patch_bwd_main(a, st)) return rc;
+  return rl_patch_bwd_wgrad(a, st);
 }

@@ -136,5 +136,11 @@ def set_attn_umma(mode: int) -> int:
     return int(load().ralenet_set_attn_umma(int(mode)))
 
 
+def set_wgrad_umma(on: bool) -> bool:
+    """weight-gradient GEMMs: True = tcgen05 kernels (wgrad_umma.cu, default), False = mma.sync kernels (wgrad.cu).
+    Same function either way; returns the previous setting."""
+    return bool(load().ralenet_set_wgrad_umma(1 if on else 0))
+
+
 def launch_count(reset: bool = False) -> int:
     return int(load().ralenet_launch_count(1 if reset else 0))

@@ -212,7 +212,13 @@ int launch_group(WgGroup& g, int total_tiles, cudaStream_t st) {
 
 // up to 4 problems sharing M; dims must all be multiples of 32 for the tensor-core path, otherwise the
 // problems are launched one by one on the FFMA kernel.
+int rl_launch_wgrad_group_umma(const RlWgradDesc* d, int n, int M, cudaStream_t st);   // wgrad_umma.cu
+
 int rl_launch_wgrad_group(const RlWgradDesc* d, int n, int M, cudaStream_t st) {
+  {
+    const int rc = rl_launch_wgrad_group_umma(d, n, M, st);    // tcgen05 kernels; 1: group not handled there
+    if (rc <= 0) return rc;
+  }
   int cnt = 0, mind = 1 << 30;
   bool aligned = true;
   for (int i = 0; i < n; ++i) {

@@ -104,6 +104,10 @@ int ralenet_attn_bwd(const rl_attn_bwd_args* a, void* stream);
  * the same function; the switch exists for A/B measurements and the agreement test.  Initial value: environment
  * variable RALENET_ATTN_UMMA.  Returns the previous mode.  Not thread-safe against running calls. */
 int ralenet_set_attn_umma(int mode);
+/* Weight-gradient GEMMs (dW += dY^T X over all tokens) of the stages with C >= 32 and of the patch layers:
+ * 1 (default) = tcgen05 kernels (wgrad_umma.cu), 0 = mma.sync kernels (wgrad.cu).  Same function; A/B switch,
+ * initial value from RALENET_WGRAD_UMMA.  Returns the previous setting. */
+int ralenet_set_wgrad_umma(int on);
 
 /* ------------------------------------------------------------------------------------------
  * Feed-forward half:  y = x + fc2(GELU(leconv(GELU(fc1(LN2(x))))))  (+ extra)

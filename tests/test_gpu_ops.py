@@ -234,6 +234,43 @@ def test_ffn_block(ops, stage, le):
         _cmp(f"{tag}/d_{k}", d[k].grad, gr[k])
 
 
+@pytest.mark.parametrize("stage", [2, 3, 4])
+@pytest.mark.parametrize("B", [5, 37])
+def test_wgrad_tcgen05_kernels_match_mma_sync_kernels(ops, stage, B):
+    """Weight-gradient GEMMs of a whole block (attention: Wp, Wq, Wkv + biases; feed-forward: W1, W2 + biases, one of
+    them tiled as its transpose) at token counts that are not multiples of the chunk / tile sizes: the tcgen05 kernels
+    (wgrad_umma.cu) and the mma.sync kernels (wgrad.cu) agree far inside the tolerance."""
+    from ecg_denoise_b200 import _lib
+    rs = np.random.RandomState(700 + stage)
+    C, H, L = O.CHANNELS[stage], O.HEADS[stage], O.LENGTHS[stage]
+    p = _block_params(rs, C, 1)
+    x = _rand(rs, B, L, C).float().cuda()
+    g = _rand(rs, B, L, C).float().cuda()
+    d = {k: v.float().cuda() for k, v in p.items()}
+    an = ("norm1.weight", "norm1.bias", "attn.qkv_proj.to_q.weight", "attn.qkv_proj.to_q.bias",
+          "attn.qkv_proj.to_kv.weight", "attn.qkv_proj.to_kv.bias", "attn.proj.weight", "attn.proj.bias")
+    fn = ("norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias",
+          "mlp.leconv.partial_conv3.weight")
+
+    def run(tc):
+        prev = _lib.set_wgrad_umma(tc)
+        try:
+            xs = x.clone().requires_grad_(True)
+            pa = [d[k].clone().requires_grad_(True) for k in an]
+            pf = [d[k].clone().requires_grad_(True) for k in fn]
+            y = ops.AttnBlockFn.apply(xs, *pa, None, H, 0, 0, ops.RL_F_PRENORM | ops.RL_F_RESIDUAL)
+            y = ops.FFNBlockFn.apply(y, *pf, None, 1, ops.RL_F_PRENORM | ops.RL_F_RESIDUAL)
+            y.backward(g)
+            torch.cuda.synchronize()
+            return [q.grad for q in pa + pf]
+        finally:
+            _lib.set_wgrad_umma(prev)
+
+    a, b = run(True), run(False)
+    for name, ta, tb in zip(an + fn, a, b):
+        _cmp(f"wgrad_tc_vs_mma/s{stage}/B{B}/d_{name}", ta, tb, rtol=5e-5)
+
+
 @pytest.mark.parametrize("stage", [0, 1, 2, 3])
 def test_patch_merge(ops, stage):
     rs = np.random.RandomState(300 + stage)

@@ -154,28 +154,31 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) wgrad_umma_kernel(const WuGrou
   umma::tc_fence_after();
   const uint32_t tb = *tmem_slot;
 
-  TokStage<TN> sa;
-  TokStage<TK> sb;
+  // register double buffer: the global loads of chunks j + 1 and j + 2 are in flight while chunk j is staged
+  TokStage<TN> sa[2];
+  TokStage<TK> sb[2];
   float bsum_a = 0.f, bsum_b = 0.f;
   Ring ring{bars, 0};
   constexpr uint32_t idesc = umma::idesc_tf32(TN, TK);
-  if (nchunk > 0) {
-    sa.load(ga, lda, rows_valid, m_begin, m_end);
-    sb.load(gb, ldb, TK, m_begin, m_end);
-  }
-  for (int j = 0; j < nchunk; ++j) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+    if (u < nchunk) {
+      sa[u].load(ga, lda, rows_valid, m_begin + u * KC, m_end);
+      sb[u].load(gb, ldb, TK, m_begin + u * KC, m_end);
+    }
+  auto step = [&](int j, TokStage<TN>& ra, TokStage<TK>& rb) {
     ring.wait_free();
     float* a_hi = ring_mem + ring.buf() * WuSmem<TK>::STAGE;
     float* a_lo = a_hi + TN * KC;
     float* b_hi = a_lo + TN * KC;
     float* b_lo = b_hi + TK * KC;
-    sa.store(a_hi, a_lo);
-    sb.store(b_hi, b_lo);
-    if (want_ba) bsum_a += sa.token_sum();
-    if (want_bb) bsum_b += sb.token_sum();
-    if (j + 1 < nchunk) {                                     // in flight during the barrier and the MMA issue
-      sa.load(ga, lda, rows_valid, m_begin + (j + 1) * KC, m_end);
-      sb.load(gb, ldb, TK, m_begin + (j + 1) * KC, m_end);
+    ra.store(a_hi, a_lo);
+    rb.store(b_hi, b_lo);
+    if (want_ba) bsum_a += ra.token_sum();
+    if (want_bb) bsum_b += rb.token_sum();
+    if (j + 2 < nchunk) {
+      ra.load(ga, lda, rows_valid, m_begin + (j + 2) * KC, m_end);
+      rb.load(gb, ldb, TK, m_begin + (j + 2) * KC, m_end);
     }
     umma::fence_async_smem();
     __syncthreads();
@@ -185,9 +188,13 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) wgrad_umma_kernel(const WuGrou
       umma::commit(bars + ring.buf());
     }
     ++ring.chunk;
+  };
+  for (int j = 0; j < nchunk; j += 2) {
+    step(j, sa[0], sb[0]);
+    if (j + 1 < nchunk) step(j + 1, sa[1], sb[1]);
   }
-  if (want_ba && sa.active()) atomicAdd(&s_ba[sa.my_row()], bsum_a);
-  if (want_bb && sb.active()) atomicAdd(&s_bb[sb.my_row()], bsum_b);
+  if (want_ba && sa[0].active()) atomicAdd(&s_ba[sa[0].my_row()], bsum_a);
+  if (want_bb && sb[0].active()) atomicAdd(&s_bb[sb[0].my_row()], bsum_b);
   if (nchunk > 0) {
     ring.wait_last();
     umma::tc_fence_after();
@@ -217,7 +224,12 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) wgrad_umma_kernel(const WuGrou
 template <int TK>
 int launch(WuGroup& g, int total_tiles, cudaStream_t st) {
   // one wave of CTAs (148 SMs), each with at least four chunks of tokens
-  int splits = (148 + total_tiles - 1) / total_tiles;
+  static const int target = [] {
+    const char* e = getenv("RALENET_WGRAD_CTAS");
+    const int v = (e && *e) ? atoi(e) : 0;
+    return v > 0 ? v : 148;
+  }();
+  int splits = (target + total_tiles - 1) / total_tiles;
   const int max_splits = (g.M + 4 * KC - 1) / (4 * KC);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

@@ -209,8 +209,19 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) wgrad_umma_kernel(const WuGrou
       float t0[16];
       umma::tmem_ld16(umma::tmem_addr(tb, c16 * 16), t0);
       if (row < rows_valid) {
+        if (so_c == 1) {
+          // a thread owns 16 consecutive columns of its row: four 16-byte vector reductions (a quarter of the L2
+          // transactions of scalar ones, which would touch 32 rows = 32 sectors per warp instruction)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) atomicAdd(orow + (size_t)(c16 * 16 + i) * so_c, t0[i]);
+          for (int i = 0; i < 16; i += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + c16 * 16 + i), "f"(t0[i]),
+                         "f"(t0[i + 1]), "f"(t0[i + 2]), "f"(t0[i + 3])
+                         : "memory");
+        } else {
+          // transposed output: the lanes (rows of the tile) are contiguous in memory, one line per warp instruction
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(orow + (size_t)(c16 * 16 + i) * so_c, t0[i]);
+        }
       }
     }
   }

@@ -10,9 +10,11 @@
 //   * both operands are token-major in global memory ([m][n], [m][k]) while the MMA wants the contraction (token)
 //     index contiguous: chunks of KC = 32 tokens are transposed on the way to shared memory (32 consecutive n of four
 //     consecutive tokens per warp load, one 16-byte K-major chunk per lane) together with their tf32 remainders;
-//   * 2-stage ring: the global loads of chunk j + 1 are in flight while chunk j is staged and its MMAs issued;
-//   * epilogue: TMEM -> registers -> fp32 red.global into dW; the bias gradient is summed from the staged
-//     registers of the dY operand.
+//   * 2-stage shared-memory ring, and the global loads of chunks j + 1 and j + 2 are in flight (registers) while
+//     chunk j is staged and its MMAs issued;
+//   * epilogue: TMEM -> registers -> fp32 red.global into dW, as 16-byte vector reductions along a row (scalar ones,
+//     one row per lane, are 32 L2 sector operations per warp instruction and took half of the kernel); the bias
+//     gradient is summed from the staged registers of the dY operand.
 // Up to 4 problems that share the token dimension and the tile width go into one launch (all weight matrices of a
 // half-block).  Shapes this kernel does not take (columns not a multiple of 32, tiny M) stay on wgrad.cu.
 #define RL_NT 512
@@ -234,13 +236,10 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) wgrad_umma_kernel(const WuGrou
 
 template <int TK>
 int launch(WuGroup& g, int total_tiles, cudaStream_t st) {
-  // one wave of CTAs (148 SMs), each with at least four chunks of tokens
-  static const int target = [] {
-    const char* e = getenv("RALENET_WGRAD_CTAS");
-    const int v = (e && *e) ? atoi(e) : 0;
-    return v > 0 ? v : 148;
-  }();
-  int splits = (target + total_tiles - 1) / total_tiles;
+  // one wave of CTAs (148 SMs), each with at least four chunks of tokens.  Measured on the training step (B = 256):
+  // 112 / 148 / 222 / 296 CTAs -> 2.266 / 2.248 / 2.290 / 2.265 ms, 64 -> 2.355, 32 -> 2.425 (the in-order side stream
+  // becomes the critical path); the SM time of these kernels (CTAs x duration) is the same at every split.
+  int splits = (148 + total_tiles - 1) / total_tiles;
   const int max_splits = (g.M + 4 * KC - 1) / (4 * KC);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

@@ -5,8 +5,8 @@
 tag=${1:-step}
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 3 --warmup 3 --graph off --no-cpu-baseline --no-profile"
-RX='regex:(attn_bwd_kernel<.int.16,|attn_bwd_kernel<.int.8,|attn_fwd_kernel<.int.16,|attn_fwd_kernel<.int.128,|ffn_bwd_kernel<.int.16,|ffn_fwd_umma_kernel<.int.128|ffn_bwd_umma_kernel<.int.128|wgrad_group_kernel<.int.64|patch_bwd_kernel<.int.32,)'
-timeout 420 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k "$RX" -s 60 -c 14 \
+RX='regex:(attn_bwd_kernel<.int.16,|attn_bwd_kernel<.int.8,|attn_fwd_kernel<.int.16,|attn_fwd_kernel<.int.128,|ffn_bwd_kernel<.int.16,|ffn_fwd_umma_kernel<.int.128|ffn_bwd_umma_kernel<.int.128|attn_fwd_umma_kernel<.int.128|attn_fwd_umma_kernel<.int.64|wgrad_umma_kernel<.int.128|wgrad_umma_kernel<.int.64|patch_bwd_kernel<.int.32,)'
+timeout 420 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k "$RX" -s 60 -c 16 \
   -o gpurun_out/${tag}_top $BENCH > gpurun_out/${tag}_ncu.log 2>&1
 ncu -i gpurun_out/${tag}_top.ncu-rep --page raw --csv > gpurun_out/${tag}_top_raw.csv 2>/dev/null
 ls -la gpurun_out | tail -8

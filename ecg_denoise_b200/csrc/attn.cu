@@ -170,6 +170,15 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   const int tid = threadIdx.x;
   RL_TS(attn, 0);
   AttnW<C>::DProj::prefetch(sw, a.wp, 1 << 30, nullptr, C);   // weights do not depend on the preceding kernels
+  {   // neither do the tensors the forward pass saved for this window: q, k, v, o, lse and the block input
+    const size_t wo = (size_t)blockIdx.x * LC;
+    prefetch_l2_block(a.q + wo, LC * 4);
+    prefetch_l2_block(a.k + wo, LC * 4);
+    prefetch_l2_block(a.v + wo, LC * 4);
+    prefetch_l2_block(a.o + wo, LC * 4);
+    prefetch_l2_block(a.x + wo, LC * 4);
+    prefetch_l2_block(a.lse + (size_t)blockIdx.x * (LC / 4), LC);
+  }
   pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
   pdl_trigger();   // let the next kernel get scheduled while this one runs
   RL_TS(attn, 1);

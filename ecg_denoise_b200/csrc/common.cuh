@@ -63,6 +63,14 @@ static inline void rl_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block
   rl_prof_pre(st);
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);      // errors surface through rl_check_launch()
 }
+// L2 prefetch of tensors that were saved by the forward pass (they sit in HBM by the time the backward reads them):
+// issued before griddepcontrol.wait, the HBM latency passes behind the tail of the preceding kernel and the loads of
+// the kernel proper hit L2.  A hint: no register, no dependency, nothing to wait for.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// `bytes` from p (128-byte lines), spread over the threads of the CTA
+__device__ __forceinline__ void prefetch_l2_block(const void* p, int bytes) {
+  for (int o = threadIdx.x * 128; o < bytes; o += RL_NT * 128) prefetch_l2(reinterpret_cast<const char*>(p) + o);
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -436,6 +444,37 @@ struct MmaTile {
         }
       }
     }
+  }
+
+  // v[r][c][e] <- src[row * ld + col] for every output element owned by this thread, in the order of epilogue2():
+  // all loads are issued back to back (one round trip to L2 / HBM instead of one per element inside an epilogue
+  // lambda).  ld and the tile origin must be even (two adjacent columns per 8-byte load).
+  __device__ __forceinline__ void gather(const float* __restrict__ src, int ld, float (&v)[RT][CT][4]) const {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const int m = row0 + r * 16 + g, n = col0 + c * 8 + 2 * t;
+        const float2 lo = __ldg(reinterpret_cast<const float2*>(src + (size_t)m * ld + n));
+        const float2 hi = __ldg(reinterpret_cast<const float2*>(src + (size_t)(m + 8) * ld + n));
+        v[r][c][0] = lo.x; v[r][c][1] = lo.y; v[r][c][2] = hi.x; v[r][c][3] = hi.y;
+      }
+  }
+  // f(row, col, value, gathered value) for every output element owned by this thread
+  template <class F>
+  __device__ __forceinline__ void epilogue2(const float (&v)[RT][CT][4], F f) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const int m = row0 + r * 16 + g, n = col0 + c * 8 + 2 * t;
+        f(m, n, acc[r][c][0], v[r][c][0]);
+        f(m, n + 1, acc[r][c][1], v[r][c][1]);
+        f(m + 8, n, acc[r][c][2], v[r][c][2]);
+        f(m + 8, n + 1, acc[r][c][3], v[r][c][3]);
+      }
   }
 
   // f(row, col, value) for every output element owned by this thread

@@ -156,6 +156,9 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
   float* s_red = s_gb + 2 * C;
   const int tid = threadIdx.x;
   WStream<HC, C, B_KN>::prefetch(sw, a.w2, 1 << 30, nullptr, HC);   // weights do not depend on the preceding kernels
+  // neither do the tensors the forward pass saved for this window (pre-activations h, block input)
+  prefetch_l2_block(a.h + (size_t)blockIdx.x * L * HC, L * HC * 4);
+  prefetch_l2_block(a.x + (size_t)blockIdx.x * L * C, L * C * 4);
   pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
   pdl_trigger();   // let the next kernel get scheduled while this one runs
   const size_t woff = (size_t)blockIdx.x * L * C;
@@ -201,7 +204,13 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
     acc.init();
     WStream<HC, C, B_KN>::template run<true>(acc, sg, LDC, sw, a.w2, 1 << 30, nullptr, HC);
     WStream<C, HC, B_KN>::prefetch(sw, a.w1, 1 << 30, nullptr, C);    // lands behind the GELU' / FIR-adjoint phase
-    acc.epilogue([&](int t, int n, float v) {
+    // the saved pre-activations of this thread's elements: one batch of loads (they come from HBM: a load per
+    // element inside the epilogue was 16 serial round trips)
+    //  (512-sample windows have 32 elements per thread: there the registers do not allow it and the loads stay inside)
+    constexpr bool BATCH = MmaTile<L, HC>::TPW * 4 <= 16;
+    float hv[MmaTile<L, HC>::RT][MmaTile<L, HC>::CT][4];
+    if (!DW && BATCH) acc.gather(hw, HC, hv);
+    acc.epilogue2(hv, [&](int t, int n, float v, float hval) {
       if (DW) {
         const float g1 = sh[t * LDH + n];
         const float p = (t > 0) ? sh[(t - 1) * LDH + n] : 0.f;
@@ -210,7 +219,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
         sd[t * LDH + n] = v * gelu_grad_f(f);          // df, finished below
       } else {
         float g1, d1;
-        gelu_both(__ldg(hw + t * HC + n), g1, d1);
+        gelu_both(BATCH ? hval : __ldg(hw + t * HC + n), g1, d1);
         if (mode == RL_LE_NONE) {
           if (FW) sg2[t * LDH + n] = g1; else g2w[t * HC + n] = g1;
           const float dh = v * d1;

@@ -345,6 +345,15 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_umma_kernel(const rl_f
 #pragma unroll
     for (int j = 0; j < C / KC; ++j) w2r[j].load(w2s + (size_t)(j * KC) * HC, HC);
   }
+  {   // the tensors the forward pass saved sit in HBM by now: pull this CTA's pre-activation slice (one 128-byte
+      // line per thread: 32 hidden units of one token) and its rows of the block input towards L2
+    const int tile_p = blockIdx.x / NSL, r_p = blockIdx.x % NSL;
+    const long long tok = (long long)tile_p * TM + ((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31);
+    if (tok < (long long)a.B * L) {
+      prefetch_l2(a.h + tok * HC + r_p * TS + (threadIdx.x >> 7) * 32);
+      if ((int)(threadIdx.x >> 7) < C / 32) prefetch_l2(a.x + tok * C + (threadIdx.x >> 7) * 32);
+    }
+  }
   pdl_wait();
   pdl_trigger();
   extern __shared__ __align__(128) float smem[];

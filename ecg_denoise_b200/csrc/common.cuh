@@ -66,7 +66,11 @@ static inline void rl_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block
 // L2 prefetch of tensors that were saved by the forward pass (they sit in HBM by the time the backward reads them):
 // issued before griddepcontrol.wait, the HBM latency passes behind the tail of the preceding kernel and the loads of
 // the kernel proper hit L2.  A hint: no register, no dependency, nothing to wait for.
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef RL_NO_L2_PREFETCH      // A/B builds; measured on the graphed step: 2.229 ms without, 2.212 ms with
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 // `bytes` from p (128-byte lines), spread over the threads of the CTA
 __device__ __forceinline__ void prefetch_l2_block(const void* p, int bytes) {
   for (int o = threadIdx.x * 128; o < bytes; o += RL_NT * 128) prefetch_l2(reinterpret_cast<const char*>(p) + o);

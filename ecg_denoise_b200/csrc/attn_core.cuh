@@ -1,11 +1,12 @@
 // attn_core.cuh -- tensor-core attention core for head_dim = 4 (model/transformer.py:289-323: softmax(0.5 q k^T +
 // R-wave bias) v, and its backward), operating on one window held in shared memory.
 //
-// head_dim 4 leaves no room for a conventional K = 16/32 tile, so the legacy m16n8k8 TF32 MMA is used with the
-// split-precision operands PACKED INTO THE UNUSED HALF of the instruction shape:
-//   * contraction over the 4 head dims (S = q k^T, dP = dO v^T):  A = [x_hi | x_lo] (k = 0..3 hi, 4..7 lo),
+// head_dim 4 leaves no room for a conventional K = 16/32 tile, so the split-precision operands are PACKED INTO THE
+// UNUSED PART of the instruction shape.  Forward (legacy m16n8k8 TF32 MMA; the backward, further down, packs fp16
+// hi/lo pairs into m16n8k16):
+//   * contraction over the 4 head dims (S = q k^T):  A = [x_hi | x_lo] (k = 0..3 hi, 4..7 lo),
 //     B = [y_hi ; y_hi] then [y_lo ; y_lo]  ->  two MMAs give (x_hi + x_lo)(y_hi + y_lo): fp32-grade logits.
-//   * contraction over 8 keys / queries (O = P v, dQ = dS k, dK = dS^T q, dV = P^T dO), N = 4 head dims:
+//   * contraction over 8 keys (O = P v), N = 4 head dims:
 //     B = [y_hi | y_lo] (n = 0..3 hi, 4..7 lo), A = p_hi then p_lo; the two column halves are added at the end.
 //     The accumulator fragment of S (rows g, g+8; cols 2t, 2t+1) is reused directly as the A fragment by
 //     contracting over the keys in the order (2t, 2t+1) -> (k = t, t+4), so P never touches shared memory.
@@ -133,177 +134,6 @@ __device__ __forceinline__ void attn_core_fwd(float* sq, const float* sk, const 
   for (int item = warp; item < NITEM; item += NW) {
     const int h = item / QT, i0 = (item % QT) * 16;
     attn_core_fwd_item<L, LDC>(sq, sk, sv, 4 * h, i0, stab + h, H, W, c0, lse_g ? lse_g + h * L : nullptr);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// backward, query-major pass: dq[i] = 0.5 sum_j ds[i,j] k[j], ds = p (dp - D); also the R-wave table gradient
-// (sum of ds over the central pairs of equal offset) into stabg (shared, pre-zeroed) when want_tab.
-template <int C, int L>
-__device__ __forceinline__ void attn_core_bwd_dq(const float* sq, const float* sk, const float* sv, const float* sdo,
-                                                 const float* sD, const float* sLse, float* sdq, const float* stab,
-                                                 float* stabg, bool want_tab, int W, int c0) {
-  constexpr int H = C / RL_HD, LDC = ld_mk(C), NW = RL_NT / 32;
-  constexpr int QT = L / 16, NITEM = H * QT;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const float qs = 0.5f * RL_LOG2E;
-  const bool sel_hi = g < 4;
-#pragma unroll 1
-  for (int item = warp; item < NITEM; item += NW) {
-    const int h = item / QT, i0 = (item % QT) * 16;
-    uint32_t qa[4], da[4];
-    {
-      const int off = (i0 + g) * LDC + 4 * h + t;
-      split_tf32(sq[off] * qs, qa[0], qa[2]);
-      split_tf32(sq[off + 8 * LDC] * qs, qa[1], qa[3]);
-      split_tf32(sdo[off], da[0], da[2]);
-      split_tf32(sdo[off + 8 * LDC], da[1], da[3]);
-    }
-    const float lse0 = sLse[h * L + i0 + g], lse1 = sLse[h * L + i0 + g + 8];
-    const float D0 = sD[h * L + i0 + g], D1 = sD[h * L + i0 + g + 8];
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const bool qcen = (W > 0) && (i0 + 16 > c0) && (i0 < c0 + W);
-    const int offA = g * LDC + 4 * h + t;                    // [key g][dim t]: B operand of the hd contractions
-    const int offB = (2 * t) * LDC + 4 * h + (g & 3);        // [key 2t][dim g&3]: B operand of the key contraction
-#pragma unroll 2
-    for (int j0 = 0; j0 < L; j0 += 8) {
-      float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-      {
-        uint32_t kh, kl, vh, vl;
-        split_tf32(sk[j0 * LDC + offA], kh, kl);
-        split_tf32(sv[j0 * LDC + offA], vh, vl);
-        const uint32_t b0[2] = {kh, kh}, b1[2] = {kl, kl}, b2[2] = {vh, vh}, b3[2] = {vl, vl};
-        mma_tf32(s, qa, b0);
-        mma_tf32(dp, da, b2);
-        mma_tf32(s, qa, b1);
-        mma_tf32(dp, da, b3);
-      }
-      const bool cen = qcen && (j0 + 8 > c0) && (j0 < c0 + W);
-      if (cen) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = i0 + g + 8 * (e >> 1), j = j0 + 2 * t + (e & 1);
-          if ((unsigned)(i - c0) < (unsigned)W && (unsigned)(j - c0) < (unsigned)W) s[e] += stab[(i - j + W - 1) * H + h];
-        }
-      }
-      float ds[4];
-      ds[0] = fast_ex2(s[0] - lse0) * (dp[0] - D0);
-      ds[1] = fast_ex2(s[1] - lse0) * (dp[1] - D0);
-      ds[2] = fast_ex2(s[2] - lse1) * (dp[2] - D1);
-      ds[3] = fast_ex2(s[3] - lse1) * (dp[3] - D1);
-      if (cen && want_tab) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = i0 + g + 8 * (e >> 1), j = j0 + 2 * t + (e & 1);
-          if ((unsigned)(i - c0) < (unsigned)W && (unsigned)(j - c0) < (unsigned)W)
-            atomicAdd(&stabg[(i - j + W - 1) * H + h], ds[e]);
-        }
-      }
-      uint32_t ah[4], al[4];
-      split_tf32(ds[0], ah[0], al[0]);
-      split_tf32(ds[2], ah[1], al[1]);
-      split_tf32(ds[1], ah[2], al[2]);
-      split_tf32(ds[3], ah[3], al[3]);
-      const uint32_t b[2] = {pack_hl(sk[j0 * LDC + offB], sel_hi), pack_hl(sk[(j0 + 1) * LDC + offB], sel_hi)};
-      mma_tf32(acc, ah, b);
-      mma_tf32(acc, al, b);
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 2);
-    if (t < 2) {
-      *reinterpret_cast<float2*>(sdq + (i0 + g) * LDC + 4 * h + 2 * t) = make_float2(0.5f * acc[0], 0.5f * acc[1]);
-      *reinterpret_cast<float2*>(sdq + (i0 + g + 8) * LDC + 4 * h + 2 * t) = make_float2(0.5f * acc[2], 0.5f * acc[3]);
-    }
-  }
-}
-
-// backward, key-major pass: dk[j] = 0.5 sum_i ds[i,j] q[i], dv[j] = sum_i p[i,j] do[i]
-// (the transposed tiles S^T = k q^T and dP^T = v dO^T are computed directly, rows = keys, cols = queries)
-template <int C, int L>
-__device__ __forceinline__ void attn_core_bwd_dkv(const float* sq, const float* sk, const float* sv, const float* sdo,
-                                                  const float* sD, const float* sLse, float* sdk, float* sdv,
-                                                  const float* stab, int W, int c0) {
-  constexpr int H = C / RL_HD, LDC = ld_mk(C), NW = RL_NT / 32;
-  constexpr int JT = L / 16, NITEM = H * JT;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const float qs = 0.5f * RL_LOG2E;
-  const bool sel_hi = g < 4;
-#pragma unroll 1
-  for (int item = warp; item < NITEM; item += NW) {
-    const int h = item / JT, j0 = (item % JT) * 16;
-    uint32_t ka[4], va[4];
-    {
-      const int off = (j0 + g) * LDC + 4 * h + t;
-      split_tf32(sk[off], ka[0], ka[2]);
-      split_tf32(sk[off + 8 * LDC], ka[1], ka[3]);
-      split_tf32(sv[off], va[0], va[2]);
-      split_tf32(sv[off + 8 * LDC], va[1], va[3]);
-    }
-    float ak[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
-    const bool kcen = (W > 0) && (j0 + 16 > c0) && (j0 < c0 + W);
-    const int offA = g * LDC + 4 * h + t;
-    const int offB = (2 * t) * LDC + 4 * h + (g & 3);
-    const float* lsep = sLse + h * L + 2 * t;
-    const float* Dp = sD + h * L + 2 * t;
-#pragma unroll 2
-    for (int i0 = 0; i0 < L; i0 += 8) {
-      float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-      {
-        uint32_t qh, ql, dh, dl;
-        split_tf32(sq[i0 * LDC + offA] * qs, qh, ql);
-        split_tf32(sdo[i0 * LDC + offA], dh, dl);
-        const uint32_t b0[2] = {qh, qh}, b1[2] = {ql, ql}, b2[2] = {dh, dh}, b3[2] = {dl, dl};
-        mma_tf32(s, ka, b0);
-        mma_tf32(dp, va, b2);
-        mma_tf32(s, ka, b1);
-        mma_tf32(dp, va, b3);
-      }
-      if (kcen && (i0 + 8 > c0) && (i0 < c0 + W)) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = i0 + 2 * t + (e & 1), j = j0 + g + 8 * (e >> 1);
-          if ((unsigned)(i - c0) < (unsigned)W && (unsigned)(j - c0) < (unsigned)W) s[e] += stab[(i - j + W - 1) * H + h];
-        }
-      }
-      const float2 ls = *reinterpret_cast<const float2*>(lsep + i0);
-      const float2 Dd = *reinterpret_cast<const float2*>(Dp + i0);
-      float p[4], ds[4];
-      p[0] = fast_ex2(s[0] - ls.x);
-      p[1] = fast_ex2(s[1] - ls.y);
-      p[2] = fast_ex2(s[2] - ls.x);
-      p[3] = fast_ex2(s[3] - ls.y);
-      ds[0] = p[0] * (dp[0] - Dd.x);
-      ds[1] = p[1] * (dp[1] - Dd.y);
-      ds[2] = p[2] * (dp[2] - Dd.x);
-      ds[3] = p[3] * (dp[3] - Dd.y);
-      uint32_t ph[4], pl[4], dh4[4], dl4[4];
-      split_tf32(p[0], ph[0], pl[0]);
-      split_tf32(p[2], ph[1], pl[1]);
-      split_tf32(p[1], ph[2], pl[2]);
-      split_tf32(p[3], ph[3], pl[3]);
-      split_tf32(ds[0], dh4[0], dl4[0]);
-      split_tf32(ds[2], dh4[1], dl4[1]);
-      split_tf32(ds[1], dh4[2], dl4[2]);
-      split_tf32(ds[3], dh4[3], dl4[3]);
-      const uint32_t bd[2] = {pack_hl(sdo[i0 * LDC + offB], sel_hi), pack_hl(sdo[(i0 + 1) * LDC + offB], sel_hi)};
-      const uint32_t bq[2] = {pack_hl(sq[i0 * LDC + offB], sel_hi), pack_hl(sq[(i0 + 1) * LDC + offB], sel_hi)};
-      mma_tf32(av, ph, bd);
-      mma_tf32(ak, dh4, bq);
-      mma_tf32(av, pl, bd);
-      mma_tf32(ak, dl4, bq);
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      ak[e] += __shfl_xor_sync(0xffffffffu, ak[e], 2);
-      av[e] += __shfl_xor_sync(0xffffffffu, av[e], 2);
-    }
-    if (t < 2) {
-      const int off = (j0 + g) * LDC + 4 * h + 2 * t;
-      *reinterpret_cast<float2*>(sdk + off) = make_float2(0.5f * ak[0], 0.5f * ak[1]);
-      *reinterpret_cast<float2*>(sdk + off + 8 * LDC) = make_float2(0.5f * ak[2], 0.5f * ak[3]);
-      *reinterpret_cast<float2*>(sdv + off) = make_float2(av[0], av[1]);
-      *reinterpret_cast<float2*>(sdv + off + 8 * LDC) = make_float2(av[2], av[3]);
-    }
   }
 }
 

@@ -56,6 +56,25 @@ def test_ctypes_structs_match_c_layout(built_lib):
             assert got[f"{sname}.{fname}"] == getattr(st, fname).offset, (sname, fname)
 
 
+def test_kernel_selection_switches_round_trip(built_lib):
+    """ralenet_set_attn_umma / ralenet_set_wgrad_umma select between two implementations of the same function; the
+    setters return the previous value, clamp bad input to the default and need no GPU."""
+    prev = built_lib.set_attn_umma(0)
+    try:
+        assert prev in (0, 1, 2)
+        assert built_lib.set_attn_umma(2) == 0
+        assert built_lib.set_attn_umma(7) == 2            # out of range -> build default (1)
+        assert built_lib.set_attn_umma(1) == 1
+    finally:
+        built_lib.set_attn_umma(prev)
+    prev = built_lib.set_wgrad_umma(False)
+    try:
+        assert built_lib.set_wgrad_umma(True) is False
+        assert built_lib.set_wgrad_umma(True) is True
+    finally:
+        built_lib.set_wgrad_umma(prev)
+
+
 def test_workspace_size_is_monotonic(built_lib):
     lib = built_lib.load()
     a = lib.ralenet_net_workspace_bytes(32, 256, 1)

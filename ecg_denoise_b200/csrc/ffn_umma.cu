@@ -279,17 +279,38 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
     }
   }
   umma::tc_fence_before();
+  // rows [r RPC, (r + 1) RPC) are finished here: their bias + residual (+ extra) terms are fetched before the
+  // cluster barrier instead of one round trip per item behind it
+  constexpr int RPC = TM / NSL, RIT = RPC * (C / 4) / RL_NT;  // rows finished by this CTA, float4 items per thread
+  static_assert(RPC * (C / 4) % RL_NT == 0, "reduce: items must tile the CTA");
+  float4 add4[RIT];
+#pragma unroll
+  for (int it = 0; it < RIT; ++it) {
+    const int i = tid + it * RL_NT;
+    const int rr = r * RPC + i / (C / 4), c = (i % (C / 4)) * 4;
+    add4[it] = a.b2 ? __ldg(reinterpret_cast<const float4*>(a.b2 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rr < nvalid) {
+      const size_t g = (tok0 + rr) * C + c;
+      if (a.flags & RL_F_RESIDUAL) {
+        const float4 x4 = __ldg(reinterpret_cast<const float4*>(a.x + g));
+        add4[it].x += x4.x; add4[it].y += x4.y; add4[it].z += x4.z; add4[it].w += x4.w;
+      }
+      if (a.extra) {
+        const float4 e4 = __ldg(reinterpret_cast<const float4*>(a.extra + g));
+        add4[it].x += e4.x; add4[it].y += e4.y; add4[it].z += e4.z; add4[it].w += e4.w;
+      }
+    }
+  }
   RL_TS(umma, 8);
   cluster.sync();
   RL_TS(umma, 9);
   {
-    constexpr int RPC = TM / NSL;                             // rows finished by this CTA
     const float* part[NSL];
 #pragma unroll
     for (int q = 0; q < NSL; ++q) part[q] = cluster.map_shared_rank(sp, q);
-    const float* b2 = a.b2;
-    const bool resid = a.flags & RL_F_RESIDUAL;
-    for (int i = tid; i < RPC * (C / 4); i += RL_NT) {
+#pragma unroll
+    for (int it = 0; it < RIT; ++it) {
+      const int i = tid + it * RL_NT;
       const int rr = r * RPC + i / (C / 4), c = (i % (C / 4)) * 4;
       if (rr >= nvalid) continue;
       const int off = rr * LDP + c;
@@ -299,20 +320,8 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
         const float4 p = *reinterpret_cast<const float4*>(part[q] + off);
         s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
       }
-      if (b2) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + c));
-        s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
-      }
-      const size_t g = (tok0 + rr) * C + c;
-      if (resid) {
-        const float4 x4 = __ldg(reinterpret_cast<const float4*>(a.x + g));
-        s.x += x4.x; s.y += x4.y; s.z += x4.z; s.w += x4.w;
-      }
-      if (a.extra) {
-        const float4 e4 = __ldg(reinterpret_cast<const float4*>(a.extra + g));
-        s.x += e4.x; s.y += e4.y; s.z += e4.z; s.w += e4.w;
-      }
-      *reinterpret_cast<float4*>(a.y + g) = s;
+      s.x += add4[it].x; s.y += add4[it].y; s.z += add4[it].z; s.w += add4[it].w;
+      *reinterpret_cast<float4*>(a.y + (tok0 + rr) * C + c) = s;
     }
   }
   RL_TS(umma, 10);

@@ -33,9 +33,10 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_fwd_kernel(const rl_patc
   float* su = smem;
   float* sw = su + 2 * rows * LDA;
   WStream<CN, CN, B_NK>::prefetch(sw, a.w, CN, nullptr, CN);   // weights do not depend on the preceding kernels
+  const size_t woff = (size_t)blockIdx.x * L * C;
+  if (a.skip) prefetch_l2_block(a.skip + woff, rows * CN * 4);    // nor does the U-skip tensor (written stages ago)
   pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
   pdl_trigger();   // let the next kernel get scheduled while this one runs
-  const size_t woff = (size_t)blockIdx.x * L * C;
   const float* xw = a.x + woff;
   {
     const float* lw = a.ln_w;
@@ -55,10 +56,9 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_fwd_kernel(const rl_patc
   WStream<CN, CN, B_NK>::template run<true>(acc, su, LDA, sw, a.w, CN, nullptr, CN);
   const float* sk = a.skip ? a.skip + woff : nullptr;
   float* yw = a.y + woff;
-  acc.epilogue([&](int r, int n, float v) {
-    if (sk) v += __ldg(sk + r * CN + n);
-    yw[r * CN + n] = v;
-  });
+  float skv[MmaTile<rows, CN>::RT][MmaTile<rows, CN>::CT][4] = {};
+  if (sk) acc.gather(sk, CN, skv);                 // one batch of loads, not one round trip per element
+  acc.epilogue2(skv, [&](int r, int n, float v, float s) { yw[r * CN + n] = v + s; });
 }
 
 template <int CN, int WIN>
@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_bwd_kernel(const rl_patc
   float* su = sg + rows * LDA;
   float* sw = su + rows * LDA;
   WStream<CN, CN, B_KN>::prefetch(sw, a.w, 1 << 30, nullptr, CN);   // weights do not depend on the preceding kernels
+  prefetch_l2_block(a.x + (size_t)blockIdx.x * a.L * a.C, rows * CN * 4);   // nor does the saved layer input
   pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
   pdl_trigger();   // let the next kernel get scheduled while this one runs
   float* s_gb = sw + patch_swf<CN>();
@@ -79,7 +80,8 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_bwd_kernel(const rl_patc
   const float* gw = a.g + woff;
   const float* g2w = a.g2 ? a.g2 + woff : nullptr;
   const float* xw = a.x + woff;
-  for (int i = tid; i < rows * CN; i += RL_NT) {
+#pragma unroll
+  for (int i = tid; i < rows * CN; i += RL_NT) {      // 4 (8) trips: all loads in flight together
     float v = __ldg(gw + i);
     if (g2w) {
       v += __ldg(g2w + i);

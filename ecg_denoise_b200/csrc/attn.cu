@@ -129,11 +129,12 @@ __global__ void __launch_bounds__(RL_NT, (NWC >= 4) ? 1 : RL_MINB) attn_fwd_kern
     RL_TS(attn, 7);
     const float* bp = a.bp;
     float* yw = a.y + woff;
-    const bool resid = a.flags & RL_F_RESIDUAL;
-    acc.epilogue([&](int t, int n, float v) {
+    // residual: one batch of loads, not one round trip per element
+    float rv[MmaTile<M, C>::RT][MmaTile<M, C>::CT][4] = {};
+    if (a.flags & RL_F_RESIDUAL) acc.gather(xw, C, rv);
+    acc.epilogue2(rv, [&](int t, int n, float v, float add) {
       v += bp ? __ldg(bp + n) : 0.f;
-      if (resid) v += __ldg(xw + t * C + n);
-      yw[t * C + n] = v;
+      yw[t * C + n] = v + add;
     });
   }
   RL_TS(attn, 8);

@@ -112,11 +112,21 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_kernel(const rl_ffn_fw
     const float* ex = a.extra ? a.extra + woff : nullptr;
     float* yw = a.y + woff;
     const bool resid = a.flags & RL_F_RESIDUAL;
-    acc.epilogue([&](int t, int n, float v) {
+    // residual (and the U-net skip of the middle block): one batch of loads, not one round trip per element
+    float rv[MmaTile<L, C>::RT][MmaTile<L, C>::CT][4] = {}, ev[MmaTile<L, C>::RT][MmaTile<L, C>::CT][4] = {};
+    if (resid) acc.gather(xw, C, rv);
+    if (ex) {
+      acc.gather(ex, C, ev);
+#pragma unroll
+      for (int r = 0; r < MmaTile<L, C>::RT; ++r)
+#pragma unroll
+        for (int c = 0; c < MmaTile<L, C>::CT; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) rv[r][c][e] += ev[r][c][e];
+    }
+    acc.epilogue2(rv, [&](int t, int n, float v, float add) {
       v += b2 ? __ldg(b2 + n) : 0.f;
-      if (resid) v += __ldg(xw + t * C + n);
-      if (ex) v += __ldg(ex + t * C + n);
-      yw[t * C + n] = v;
+      yw[t * C + n] = v + add;
     });
   }
 }

@@ -75,6 +75,21 @@ def test_kernel_selection_switches_round_trip(built_lib):
         built_lib.set_wgrad_umma(prev)
 
 
+def test_windows_per_record_matches_the_reference_cut(built_lib):
+    """record -> window cut of the reference (local_utils/local_utils.py:53: range(0, len - window + 1, stride)): the
+    host-side count the inference pipeline sizes its buffers with, checked against the Python range for the
+    BASELINE.json record (650000 samples -> 2539 windows of 256, 5077 at stride 128) and edge cases."""
+    from ecg_denoise_b200 import inference
+    assert inference.windows_per_record(650000, 256, 256) == 2539
+    assert inference.windows_per_record(650000, 256, 128) == 5077
+    rs = np.random.RandomState(0)
+    for _ in range(200):
+        T, W, st = int(rs.randint(1, 5000)), int(rs.choice([16, 256, 512])), int(rs.randint(1, 600))
+        assert inference.windows_per_record(T, W, st) == len(range(0, T - W + 1, st)), (T, W, st)
+    assert inference.windows_per_record(255, 256, 256) == 0      # shorter than one window
+    assert inference.windows_per_record(256, 256, 256) == 1
+
+
 def test_workspace_size_is_monotonic(built_lib):
     lib = built_lib.load()
     a = lib.ralenet_net_workspace_bytes(32, 256, 1)

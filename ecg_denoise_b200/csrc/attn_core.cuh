@@ -155,7 +155,8 @@ __device__ __forceinline__ void attn_core_fwd(float* sq, const float* sk, const 
 // are CAS loops): the warps that work on the same head walk the query blocks in a rotated order -- warp with key tile
 // jt visits query block (jt + step) mod NQB -- and meet at a named barrier after every step, so at any time each
 // query block of a head has exactly one writer.
-// so S and dP are computed once instead of twice and no operand is split inside the loop.
+// S and dP are computed once (a query-major pass for dq plus a key-major pass for dk, dv computed them twice) and no
+// operand is split inside the loop.
 #include <cuda_fp16.h>
 
 __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {

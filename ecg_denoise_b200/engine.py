@@ -46,6 +46,7 @@ class NetPlan:
         self.pe_L0 = None
         self.le_mode = 0
         self.reduce_fn: Optional[Callable[[torch.Tensor], None]] = None   # DP all-reduce of BN stats
+        self.last_ws_bytes = 0          # size of the workspace the most recent forward used (tests)
 
     # -- flattening ------------------------------------------------------------------------------
     def _aliased(self) -> bool:
@@ -55,9 +56,9 @@ class NetPlan:
         ps = list(self.net.parameters())
         if len(ps) != len(self.params):
             return False
-        for i in (0, len(ps) // 2, len(ps) - 1):
-            p = ps[i]
-            if p is not self.params[i] or p.data_ptr() != base + 4 * self.offsets[i] or p.device != self.flat.device:
+        dev = self.flat.device
+        for p, q, o in zip(ps, self.params, self.offsets):      # ~300 integer compares
+            if p is not q or p.data_ptr() != base + 4 * o or p.device != dev:
                 return False
         return True
 
@@ -167,26 +168,35 @@ class NetPlan:
             self._rg_sig = sig
 
     def attach_grads(self):
-        """make every trainable Parameter's .grad a view of the flat gradient buffer.
-        Returns True if the buffer had to be zeroed (grads were None)."""
+        """make every trainable Parameter's .grad a view of the flat gradient buffer.  A parameter whose .grad is
+        None (optimizer.zero_grad(set_to_none=True), a newly unfrozen parameter) gets its slice zeroed; a foreign
+        .grad tensor is folded into its slice; slices that are already aliased keep what they have accumulated.
+        Returns True if anything had to be attached."""
         fresh = False
+        base = self.flat_grad.data_ptr()
+        todo = []
         for p, o in zip(self.params, self.offsets):
             if not p.requires_grad:
                 continue
             g = p.grad
-            if g is None or g.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
-                fresh = True
-                break
-        if fresh:
-            # standard case after optimizer.zero_grad(set_to_none=True): start from zeros
-            keep = [(p, p.grad) for p in self.params if p.requires_grad and p.grad is not None
-                    and p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * self.offsets[self._index[id(p)]]]
-            self.flat_grad.zero_()
-            for p, o in zip(self.params, self.offsets):
-                if p.requires_grad:
-                    p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
-            for p, g in keep:                     # foreign grads that existed: fold them in
-                p.grad.add_(g)
+            if g is None or g.data_ptr() != base + 4 * o:
+                todo.append((p, o, g))
+        if not todo:
+            return False
+        fresh = True
+        n_train = sum(1 for p in self.params if p.requires_grad)
+        if len(todo) == n_train and all(g is None for _, _, g in todo):
+            self.flat_grad.zero_()          # the standard case after zero_grad(set_to_none=True): one memset
+            for p, o, _ in todo:
+                p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+            return fresh
+        for p, o, g in todo:
+            view = self.flat_grad[o:o + p.numel()].view(p.shape)
+            if g is None:
+                view.zero_()
+            else:
+                view.copy_(g)
+            p.grad = view
         return fresh
 
     def cfg(self, B: int, L0: int, training: bool, save: bool, ws: torch.Tensor):
@@ -214,36 +224,84 @@ def _call(name, *args):
     _lib.check(getattr(_lib.load(), name)(*args))
 
 
+class _WsLease:
+    """a workspace buffer borrowed from the plan's pool; returned when the last reference (the autograd node of the
+    forward that filled it) is released.  Keeps ralenet.forward from allocating a new 466 MB buffer per call."""
+    __slots__ = ("buf", "pool")
+
+    def __init__(self, buf, pool):
+        self.buf, self.pool = buf, pool
+
+    def __del__(self):
+        try:
+            if len(self.pool) < 4:
+                self.pool.append(self.buf)
+        except Exception:      # noqa: BLE001 -- interpreter shutdown
+            pass
+
+
+def _lease_ws(plan: NetPlan, nbytes: int, device) -> _WsLease:
+    # one pool per (plan, stream): a returned buffer is only handed to work enqueued on the same stream, which
+    # orders the reuse after the kernels that last touched it
+    pool = plan.__dict__.setdefault("_ws_pools", {}).setdefault((str(device), _stream()), [])
+    for i, b in enumerate(pool):
+        if b.numel() == nbytes:
+            return _WsLease(pool.pop(i), pool)
+    del pool[:]                                   # another shape: drop the cached buffers
+    return _WsLease(torch.empty(nbytes, device=device, dtype=torch.uint8), pool)
+
+
+def _check_input(x):
+    x = _chk(x, "x")
+    if x.dim() != 3 or x.shape[1] != 2:
+        raise _lib.RalenetError(f"ralenet expects (B, 2, L) windows (conv1 is Conv1d(2, 8, 3), "
+                                f"model/transformer.py:571); got {tuple(x.shape)}")
+    return x
+
+
+def _forward_impl(plan: NetPlan, x, save: bool):
+    B, _, L0 = x.shape
+    plan.ensure(x.device)
+    plan.refresh_requires_grad()
+    training = plan.net.training
+    lease = _lease_ws(plan, workspace_bytes(B, L0, save), x.device)
+    cfg = plan.cfg(B, L0, training, save, lease.buf)
+    out = torch.empty(B, 2, L0, device=x.device, dtype=torch.float32)
+    st = ctypes.c_void_p(_stream())
+    if training:
+        _call("ralenet_net_fwd_stats", ctypes.byref(cfg), ctypes.byref(plan.P), ctypes.c_void_p(x.data_ptr()), st)
+        if plan.reduce_fn is not None:
+            plan.reduce_fn(plan.bn_stats[:17])
+    _call("ralenet_net_fwd", ctypes.byref(cfg), ctypes.byref(plan.P), ctypes.c_void_p(x.data_ptr()),
+          ctypes.c_void_p(out.data_ptr()), st)
+    return out, lease, training
+
+
+def forward_no_grad(plan: NetPlan, x):
+    """ralenet.forward without an autograd node (torch.no_grad() / nothing requires grad): nothing is saved, the
+    workspace is the 7-tensors-per-window ping/pong form (`save = 0` of net.cu::carve)."""
+    x = _check_input(x)
+    out, lease, _ = _forward_impl(plan, x, save=False)
+    plan.last_ws_bytes = lease.buf.numel()
+    return out
+
+
 class RalenetFn(torch.autograd.Function):
     """ralenet.forward (model/transformer.py:621-667) as one autograd node.
     `anchor` is a dummy leaf that requires grad whenever any parameter does, so that autograd calls
     backward even when x itself needs no gradient; parameter gradients are accumulated into the
-    Parameters' .grad views of the flat gradient buffer as a side effect."""
+    Parameters' .grad views of the flat gradient buffer as a side effect.  (Grad mode is decided by the caller,
+    _RalenetBase.forward: inside Function.forward it is always off.)"""
 
     @staticmethod
     def forward(ctx, x, anchor, plan: NetPlan):
-        x = _chk(x, "x")
-        B, Cin, L0 = x.shape
-        if Cin != 2:
-            raise _lib.RalenetError(f"ralenet expects (B, 2, L) windows (conv1 is Conv1d(2, 8, 3), "
-                                    f"model/transformer.py:571); got {tuple(x.shape)}")
-        plan.ensure(x.device)
-        plan.refresh_requires_grad()
-        net = plan.net
-        training = net.training
+        x = _check_input(x)
+        B, _, L0 = x.shape
         save = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
-        ws = torch.empty(workspace_bytes(B, L0, save), device=x.device, dtype=torch.uint8)
-        cfg = plan.cfg(B, L0, training, save, ws)
-        out = torch.empty(B, 2, L0, device=x.device, dtype=torch.float32)
-        st = ctypes.c_void_p(_stream())
-        if training:
-            _call("ralenet_net_fwd_stats", ctypes.byref(cfg), ctypes.byref(plan.P), ctypes.c_void_p(x.data_ptr()), st)
-            if plan.reduce_fn is not None:
-                plan.reduce_fn(plan.bn_stats[:17])
-        _call("ralenet_net_fwd", ctypes.byref(cfg), ctypes.byref(plan.P), ctypes.c_void_p(x.data_ptr()),
-              ctypes.c_void_p(out.data_ptr()), st)
+        out, lease, training = _forward_impl(plan, x, save)
+        plan.last_ws_bytes = lease.buf.numel()
         if save:
-            ctx.plan, ctx.ws, ctx.shape, ctx.training = plan, ws, (B, L0), training
+            ctx.plan, ctx.ws, ctx.shape, ctx.training = plan, lease, (B, L0), training
             # BN stats of THIS forward are needed by its backward; keep a private copy
             ctx.bn_stats = plan.bn_stats.clone() if training else None
             ctx.save_for_backward(x)
@@ -255,10 +313,13 @@ class RalenetFn(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         B, L0 = ctx.shape
         dout = _chk(dout, "grad_output")
+        plan.ensure(x.device)
         plan.attach_grads()
         if ctx.bn_stats is not None:
             plan.bn_stats[:17].copy_(ctx.bn_stats[:17])
-        cfg = plan.cfg(B, L0, ctx.training, True, ctx.ws)
+        # the saved activations are only read by the backward kernels (their scratch is a separate part of the
+        # workspace), so the node can be differentiated again under retain_graph=True: the lease lives as long as ctx
+        cfg = plan.cfg(B, L0, ctx.training, True, ctx.ws.buf)
         st = ctypes.c_void_p(_stream())
         _call("ralenet_net_bwd", ctypes.byref(cfg), ctypes.byref(plan.P), ctypes.byref(plan.G),
               ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(dout.data_ptr()), st)
@@ -267,7 +328,6 @@ class RalenetFn(torch.autograd.Function):
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         _call("ralenet_net_bwd_stem", ctypes.byref(cfg), ctypes.byref(plan.P), ctypes.byref(plan.G),
               ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(dx.data_ptr() if dx is not None else None), st)
-        ctx.ws = None
         return dx, None, None
 
 

@@ -17,7 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib, ops
-from ..engine import NetPlan, RalenetFn
+from ..engine import NetPlan, RalenetFn, forward_no_grad
 
 
 def _unsupported(what: str):
@@ -352,12 +352,28 @@ class _RalenetBase(nn.Module):
         object.__setattr__(self, "_plan", NetPlan(self))
         object.__setattr__(self, "_anchor", None)
 
+    # the plan holds ctypes pointer tables and device buffers that belong to THIS instance: copies and pickles
+    # (copy.deepcopy for EMA / best-model snapshots, torch.save(model)) drop it and rebuild it lazily
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_plan", None)
+        state.pop("_anchor", None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._init_plan()
+
     def forward(self, x):
         if not x.is_cuda:
             raise _lib.RalenetError(
                 "ecg_denoise_b200 ralenet.forward needs a CUDA tensor on a B200: there is no CPU fallback "
                 "(move model and data with .cuda(), as denoise_train.py:20,49 does)")
         rg = any(p.requires_grad for p in self.parameters())
+        if not torch.is_grad_enabled() or not (rg or x.requires_grad):
+            # eval under torch.no_grad() (test_cls.py:166-214, inference.denoise_records): no autograd node,
+            # nothing saved for a backward that cannot happen
+            return forward_no_grad(self._plan, x)
         a = self._anchor
         if a is None or a.device != x.device or a.requires_grad != rg:
             a = torch.zeros(1, device=x.device, requires_grad=rg)

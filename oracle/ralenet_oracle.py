@@ -417,6 +417,17 @@ def mse_loss_fwd_bwd(pred: Tensor, target: Tensor):
     return (d * d).mean(), d * (2.0 / d.numel())
 
 
+def weighted_mse_loss_fwd_bwd(pred: Tensor, target: Tensor, w: Tensor):
+    """the north star's R-wave-weighted reconstruction loss, an opt-in EXTENSION with no counterpart in the
+    reference (the reference's loss is plain F.mse_loss, denoise_train.py:53):
+        loss = mean_{b,i} w[i] (pred[b,i] - target[b,i])^2,   dL/dpred = 2 w[i] (pred - target) / numel,
+    w a per-position weight over the flattened (lead, sample) axis of a window; w == 1 is F.mse_loss exactly."""
+    B = pred.shape[0]
+    d = (pred - target).reshape(B, -1)
+    wv = w.reshape(1, -1).to(d.dtype)
+    return (wv * d * d).mean(), (wv * d * (2.0 / d.numel())).reshape(pred.shape)
+
+
 def RMSE(y: Tensor, y_pred: Tensor) -> Tensor:
     """local_utils/evaluate.py:27-29."""
     d = (y.flatten(1) - y_pred.flatten(1))

@@ -262,3 +262,56 @@ def test_kernel_gelu_formula_matches_exact_erf_gelu():
     dg64 = cdf64 + xd * np.exp(-0.5 * xd * xd) / np.sqrt(2 * np.pi)
     assert np.abs(g - g64).max() < 1e-6
     assert np.abs(dg - dg64).max() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------
+# round 2: host-side behaviour of the module mirror that needs no GPU
+def test_ralenet_deepcopy_and_pickle():
+    """copy.deepcopy (EMA / best-model snapshots) and torch.save(model) work like on the reference's modules; the
+    copy gets its own plan (ctypes pointer tables are never copied)."""
+    import copy
+    import io
+    from ecg_denoise_b200.model import ralenet_12leads, transformer
+    m = transformer.ralenet(high_level_enhence=True)
+    m2 = copy.deepcopy(m)
+    assert m2._plan is not m._plan and m2._plan.net is m2
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m3 = torch.load(buf, weights_only=False)
+    assert list(m3.state_dict().keys()) == list(m.state_dict().keys()) and m3._plan.net is m3
+    w = ralenet_12leads.newrale(ralenet_12leads.ralenet(high_level_enhence=True))
+    w2 = copy.deepcopy(w)
+    assert w2.rale._plan.net is w2.rale
+
+
+def test_flat_parameter_plan_tracks_every_parameter_and_partial_grads():
+    """NetPlan (host logic only, on CPU tensors): parameters become views of one flat buffer; re-assigning ANY
+    parameter's storage is detected; attach_grads() zeroes only the slices whose .grad is missing and folds a
+    foreign .grad in, keeping what the other slices have accumulated."""
+    from ecg_denoise_b200.model import transformer
+    m = transformer.ralenet(high_level_enhence=True)
+    plan = m._plan
+    dev = torch.device("cpu")
+    plan.ensure(dev)
+    assert plan._aliased()
+    ps = list(m.parameters())
+    assert all(p.data_ptr() == plan.flat.data_ptr() + 4 * o for p, o in zip(ps, plan.offsets))
+    victim = ps[17]                                     # not one of the three the old check sampled
+    victim.data = victim.data.clone()
+    assert not plan._aliased()
+    plan.ensure(dev)
+    assert plan._aliased()
+    assert plan.attach_grads() is True                  # all None -> one memset, every grad aliased
+    assert plan.attach_grads() is False
+    plan.flat_grad.fill_(1.0)
+    a, b, c = ps[3], ps[40], ps[77]
+    a.grad = None
+    b.grad = torch.full_like(b, 5.0)                    # foreign tensor
+    assert plan.attach_grads() is True
+    assert float(a.grad.abs().max()) == 0.0
+    assert float((b.grad - 5.0).abs().max()) == 0.0
+    assert float((c.grad - 1.0).abs().max()) == 0.0     # untouched slice kept its accumulated value
+    assert a.grad.data_ptr() == plan.flat_grad.data_ptr() + 4 * plan.offsets[3]

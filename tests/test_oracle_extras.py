@@ -71,3 +71,62 @@ def test_snr_mix_oracle_matches_reference(gold, dtype):
     d, n = data.double().reshape(6, -1), (out.double() - data.double()).reshape(6, -1)
     got = 10 * torch.log10((d ** 2).mean(1) / (n ** 2).mean(1))
     assert torch.allclose(got, snr.double(), atol=1e-3)
+
+
+@pytest.mark.parametrize("tag", ["rpos", "rpos_edge"])
+def test_rpos_block_oracle_matches_reference(gold, tag):
+    """RelativePositionEmbedding.forward(R_pos) (model/transformer.py:542-543): the W x W bias block sits at offset
+    R_pos - W//2 instead of the centre; a whole TransformerBlock driven by that mask, forward and backward."""
+    p = {str(k): _t(gold[f"{tag}/p/{k}"]) for k in gold[f"{tag}/keys"]}
+    x, gy, table = _t(gold[f"{tag}/x"]), _t(gold[f"{tag}/gy"]), _t(gold[f"{tag}/table"])
+    W, L, H = 16, 128, 4
+    c0 = int(gold[f"{tag}/R_pos"]) - W // 2
+    _close(O.rw_bias_dense(table, W, L, c0).unsqueeze(0), gold[f"{tag}/dense_mask"])
+    x1, asaved = O.attn_block_fwd(x, p, H, table, W, c0)
+    y, fsaved = O.ffn_block_fwd(x1, p)
+    _close(y, gold[f"{tag}/y"])
+    d1, gr = O.ffn_block_bwd(gy, fsaved, p)
+    dx, gra = O.attn_block_bwd(d1, asaved, p, H, table, W, c0)
+    gr.update(gra)
+    _close(dx, gold[f"{tag}/dx"])
+    _close(gr["table"], gold[f"{tag}/d_table"], 1e-9)
+    for k in p:
+        _close(gr[k].reshape(p[k].shape), gold[f"{tag}/g/{k}"], 1e-9)
+
+
+def test_rpos_mirror_builds_the_reference_mask(gold):
+    """the module mirror's RelativePositionEmbedding.forward(R_pos) returns the reference's dense mask (CPU: the
+    mask itself is plain torch; the kernels read the table and the offset instead)."""
+    from ecg_denoise_b200.model.transformer import RelativePositionEmbedding
+    rw = RelativePositionEmbedding(16, 128, 4).double()
+    rw.relative_position_bias_table.data = _t(gold["rpos/table"])
+    for tag in ("rpos", "rpos_edge"):
+        m = rw(int(gold[f"{tag}/R_pos"]))
+        _close(m.detach(), gold[f"{tag}/dense_mask"])
+        assert m._rw_src[1] == int(gold[f"{tag}/R_pos"]) - 8
+
+
+def test_records_to_windows_oracle_matches_reference_np_norm_and_cut(gold):
+    """per-lead z-normalisation = the reference's np_norm (local_utils.py:261-266, population std, no epsilon) and the
+    cut = its `signal[i:i+256, :]` over `range(0, T, 256)` (:53), both taken from the reference's own text."""
+    x = _t(gold["records/x"])
+    assert list(gold["records/cut"]) == [0, 650000, 256, 256]
+    win, _ = O.records_to_windows(x.double(), 256, 256)
+    _close(win, gold["records/windows"], 1e-12)
+    win32, _ = O.records_to_windows(x, 256, 256)
+    _close(win32, gold["records/windows"], 2e-5)
+
+
+def test_weighted_loss_reduces_to_mse_and_matches_autograd():
+    g = torch.Generator().manual_seed(3)
+    pred = torch.randn(5, 2, 256, generator=g, dtype=torch.float64, requires_grad=True)
+    tgt = torch.randn(5, 2, 256, generator=g, dtype=torch.float64)
+    w = torch.rand(512, generator=g, dtype=torch.float64) * 3 + 0.1
+    l1, d1 = O.weighted_mse_loss_fwd_bwd(pred.detach(), tgt, torch.ones(512, dtype=torch.float64))
+    l0, d0 = O.mse_loss_fwd_bwd(pred.detach(), tgt)
+    assert torch.equal(l1, l0) and torch.equal(d1, d0)
+    lw, dw = O.weighted_mse_loss_fwd_bwd(pred.detach(), tgt, w)
+    ref = (w.view(1, 2, 256) * (pred - tgt) ** 2).mean()
+    ref.backward()
+    _close(lw.reshape(1), ref.detach().reshape(1).numpy())
+    _close(dw, pred.grad.numpy())

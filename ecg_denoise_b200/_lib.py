@@ -104,6 +104,12 @@ def load():
     for name in ("ralenet_adam", "ralenet_adam_dev"):
         getattr(lib, name).argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64] + [ctypes.c_float] * 4 + [
             ctypes.c_int32 if name == "ralenet_adam" else ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p]
+    lib.ralenet_comm_bytes.restype = ctypes.c_uint64
+    lib.ralenet_comm_bytes.argtypes = [ctypes.c_uint64]
+    lib.ralenet_comm_exchange.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32,
+                                          ctypes.c_void_p]
+    lib.ralenet_comm_allreduce_adam.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_float] * 4 + [
+        ctypes.c_void_p, ctypes.c_float, ctypes.c_int32, ctypes.c_void_p]
     if lib.ralenet_abi_version() != CONSTS["RL_ABI_VERSION"]:
         raise RalenetError("libralenet_b200.so ABI version does not match include/ralenet_b200.h; rebuild")
     _lib = lib

@@ -92,6 +92,21 @@ class NetPlan:
         self.bn_stats = torch.zeros(64, device=device, dtype=torch.float32)
         self._build_tables()
 
+    def rebind_grad(self, buf: torch.Tensor):
+        """move the flat gradient buffer into caller-provided memory (the symmetric buffer of comm.SymmComm, so the
+        backward kernels accumulate straight into peer-visible memory); existing gradients are carried over."""
+        assert buf.numel() == self.n_flat and buf.dtype == torch.float32 and buf.device == self.flat.device
+        if self.flat_grad is not None and buf.data_ptr() == self.flat_grad.data_ptr():
+            return
+        with torch.no_grad():
+            buf.copy_(self.flat_grad)
+            old_base = self.flat_grad.data_ptr()
+            for p, o in zip(self.params, self.offsets):
+                if p.grad is not None and p.grad.data_ptr() == old_base + 4 * o:
+                    p.grad = buf[o:o + p.numel()].view(p.shape)
+        self.flat_grad = buf
+        self._build_tables()
+
     def _ptr_of(self, p: Optional[torch.Tensor], grad: bool):
         if p is None:
             return None
@@ -359,6 +374,10 @@ class FusedTrainer:
         self.graph = None
         self.m = self.v = self.step_dev = None
         self._static = None
+        # exchange steps: hand-written kernels over symmetric (peer / multicast) memory by default (comm.cu);
+        # RALENET_COMM=nccl keeps the three torch.distributed all-reduces (the round-1 path, kept for A/B)
+        self.comm = None
+        self.comm_mode = os.environ.get("RALENET_COMM", "symm")
 
     def _allreduce(self, t: torch.Tensor):
         torch.distributed.all_reduce(t, group=self.pg)
@@ -373,6 +392,21 @@ class FusedTrainer:
             self.v = torch.zeros_like(plan.flat)
             self.step_dev = torch.zeros(1, device=x.device, dtype=torch.int32)
         plan.reduce_fn = self._allreduce if self.world > 1 else None
+        if self.world > 1 and self.comm_mode != "nccl":
+            comm = getattr(plan, "_comm", None)
+            if comm is None or comm.n != plan.n_flat or comm.device != x.device:
+                from .comm import SymmComm
+                try:
+                    comm = SymmComm.create(plan.n_flat, x.device, self.pg)
+                except Exception as e:      # noqa: BLE001 -- no symmetric memory on this system: NCCL all-reduces
+                    import warnings
+                    warnings.warn(f"FusedTrainer: symmetric-memory exchange unavailable ({type(e).__name__}: {e}); "
+                                  "using NCCL all-reduces")
+                    comm, self.comm_mode = None, "nccl"
+                plan._comm = comm
+            self.comm = comm
+            if comm is not None:
+                plan.rebind_grad(comm.grad)
         # frozen parameters must not move: mask = requires_grad
         if any(not p.requires_grad for p in plan.params):
             mask = torch.zeros_like(plan.flat)
@@ -422,6 +456,23 @@ class FusedTrainer:
 
         if self.world == 1:
             return [("compute", lambda: (seg_a(), seg_b(), seg_c(), seg_d()))]
+
+        if self.comm is not None:
+            comm = self.comm
+
+            def fused():
+                # the whole data-parallel step as plain kernel launches: no NCCL node, one CUDA graph
+                seg_a()
+                comm.exchange(0, plan.bn_stats[:17])
+                seg_b()
+                plan.bn_stats[48:49].copy_(self._res[0])      # the loss rides along with the 16 backward sums
+                comm.exchange(1, plan.bn_stats[32:49])
+                self._res[0].copy_(plan.bn_stats[48:49])
+                seg_c()
+                if self.mask is not None:
+                    plan.flat_grad.mul_(self.mask)
+                comm.allreduce_adam(plan.flat, self.m, self.v, self.step_dev, self.lr, self.betas, self.eps, 1.0)
+            return [("compute", fused)]
 
         def ar_bwd_stats():
             # the 16 BN backward sums and the loss share one all-reduce (slot 48 of bn_stats is free)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RL_ABI_VERSION 2
+#define RL_ABI_VERSION 3
 
 enum {
   RL_OK = 0,
@@ -370,6 +370,37 @@ int ralenet_snr_mix(const float* data, const float* noise, const float* snr_db, 
  *   dW[n*K + k] += sum_m dY[m*ldy + n] * X[m*ldx + k],   db[n] += sum_m dY[m*ldy + n]   (db may be NULL) */
 int ralenet_wgrad(const float* dY, int32_t ldy, const float* X, int32_t ldx, int32_t M, int32_t N, int32_t K,
                   float* dW, float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel exchange steps over NVLink / NVSwitch peer memory (comm.cu).  Net-new: the reference is
+ * single-GPU (main.py:1-3); the contract is "N ranks on a sharded batch == one process on the global batch"
+ * (SURVEY.md section 8e): BatchNorm statistics of the stem (model/transformer.py:570-574) summed over the ranks in
+ * forward and backward, and ONE sum of the flat gradient buffer fused in front of Adam (denoise_train.py:57).
+ * Every rank owns one symmetric buffer of ralenet_comm_bytes(n) bytes, allocated and peer-mapped by the HOST
+ * (e.g. torch.distributed._symmetric_memory; the library never allocates): its first n floats are the flat gradient
+ * buffer the backward kernels accumulate into, the rest (exchange slots, barrier flags) must start zeroed.
+ * peer[i] = address of rank i's buffer in THIS process (peer[rank] = the local buffer), mc = multicast (NVLS) mapping
+ * of the same buffers or NULL, epoch = 2 + RL_COMM_MAXG zero-initialised uint32 counters in local device memory.
+ * All ranks must issue the same sequence of comm calls.  Pure kernel launches: capturable in CUDA graphs.
+ * ------------------------------------------------------------------------------------------ */
+#define RL_COMM_MAXW 8
+#define RL_COMM_MAXG 128
+typedef struct {
+  int32_t world, rank;
+  void* peer[RL_COMM_MAXW];
+  void* mc;
+  uint64_t n;                  /* floats of the gradient region (multiple of 4)                  */
+  uint32_t* epoch;
+} rl_comm;
+uint64_t ralenet_comm_bytes(uint64_t n);
+/* vals[0:n] (local device memory, n <= 32) <- sum over the ranks, added in rank order (bit-identical on every rank).
+ * set 0 / 1 = two independent slot sets (forward statistics / backward sums). */
+int ralenet_comm_exchange(const rl_comm* c, int32_t set, float* vals, int32_t n, void* stream);
+/* gradient all-reduce (sum) fused with flat Adam: reduce-scatter + broadcast through multimem.ld_reduce / multimem.st
+ * (peer loads / stores when mc == NULL), then p, m, v updated from the local copy of the sum * gscale; *step_dev is
+ * incremented first (as ralenet_adam_dev).  grid = CTAs (<= RL_COMM_MAXG, the same on every rank; 0 = default). */
+int ralenet_comm_allreduce_adam(const rl_comm* c, float* p, float* m, float* v, float lr, float beta1, float beta2,
+                                float eps, int32_t* step_dev, float gscale, int32_t grid, void* stream);
 
 /* Per-launch timing for bench.py's roofline pass: after ralenet_profile_begin(stream) every kernel this
  * library launches is followed by a CUDA event on `stream`; ralenet_profile_end() waits for the last one and

@@ -47,14 +47,18 @@ def main():
         m_1, l_1 = run(torch.from_numpy(noisy).to(dev), torch.from_numpy(clean).to(dev), 1)
         worst = 0.0
         for (n, p), (_, q) in zip(m_dp.named_parameters(), m_1.named_parameters()):
-            if n.endswith("to_kv.bias"):
-                continue          # zero-gradient key bias: Adam amplifies rounding noise (see tests/test_gpu_net.py)
             a, b = p.detach().double().cpu().numpy(), q.detach().double().cpu().numpy()
+            if n.endswith("to_kv.bias"):
+                # key half: exact gradient 0 (softmax shift invariance), Adam normalises rounding noise -> not
+                # comparable; the value half is compared (see tests/test_gpu_net.py)
+                a, b = a[a.size // 2:], b[b.size // 2:]
             e = np.max(np.abs(a - b) / (np.abs(b) + np.sqrt((b * b).mean()) + 1e-30))
             worst = max(worst, e)
         bn_d, bn_1 = m_dp.conv1[2], m_1.conv1[2]
         e_bn = float((bn_d.running_var - bn_1.running_var).abs().max())
         ok = worst < 1e-3 and np.allclose(l_dp, l_1, rtol=1e-4) and e_bn < 1e-5
+        comm = getattr(m_dp._plan, "_comm", None)
+        print(f"dp_check exchange path: {comm.kind if comm is not None else 'NCCL all-reduce'}")
         print(f"dp_check world={world} graph={use_graph}: losses dp {l_dp} single {l_1}; worst param rel err {worst:.2e}; "
               f"bn running_var diff {e_bn:.2e} -> {'OK' if ok else 'FAIL'}")
     dist.barrier()

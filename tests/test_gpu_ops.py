@@ -582,3 +582,53 @@ def test_tcgen05_block_kernels_vs_oracle_large_batch(ops, stage):
         _cmp(f"{tag}/d_{k}", d[k].grad, gr[k].reshape(p[k].shape))
     if W:
         _cmp(tag + "/d_table", tt.grad, gr["table"])
+
+
+def test_comm_kernels_two_ranks_on_one_gpu():
+    """The exchange kernels of comm.cu (BatchNorm statistic sums; gradient reduce-scatter + broadcast fused with Adam)
+    with TWO ranks emulated on one GPU: two "symmetric" buffers in the same memory, each rank's kernels on its own
+    stream, spinning on each other's flags exactly as two GPUs would over NVLink (peer-pointer variant; the multimem
+    variant needs a real multicast mapping and is covered by tests/dp_check.py on >= 2 GPUs).  Checks: sums equal and
+    bit-identical on both ranks, Adam trajectory == torch.optim.Adam on the summed gradient, three consecutive calls
+    (epoch counters / flag reuse)."""
+    from ecg_denoise_b200.comm import SymmComm
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n = 4 * 25_003
+    floats = SymmComm.nbytes(n) // 4
+    bufs = [torch.zeros(floats, device=dev) for _ in range(2)]
+    ptrs = [b.data_ptr() for b in bufs]
+    comms = [SymmComm(n, dev, ptrs, r, bufs[r]) for r in range(2)]
+    for c in comms:
+        c.grid = 24
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    g = torch.Generator(device="cpu").manual_seed(5)
+    p0 = torch.randn(n, generator=g)
+    ps = [p0.clone().to(dev) for _ in range(2)]
+    ms = [torch.zeros(n, device=dev) for _ in range(2)]
+    vs = [torch.zeros(n, device=dev) for _ in range(2)]
+    steps = [torch.zeros(1, device=dev, dtype=torch.int32) for _ in range(2)]
+    ref_p = torch.nn.Parameter(p0.clone().double())
+    opt = torch.optim.Adam([ref_p], lr=1e-3)
+    for it in range(3):
+        vals = [torch.randn(17, generator=g).to(dev) for _ in range(2)]
+        want = (vals[0].double() + vals[1].double()).cpu()
+        grads = [torch.randn(n, generator=g) * (1 + it) for _ in range(2)]
+        for r in range(2):
+            comms[r].grad.copy_(grads[r].to(dev))
+        torch.cuda.synchronize()
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                comms[r].exchange(it % 2, vals[r])
+                comms[r].allreduce_adam(ps[r], ms[r], vs[r], steps[r], 1e-3, (0.9, 0.999), 1e-8, 0.5)
+        torch.cuda.synchronize()
+        assert torch.equal(vals[0], vals[1])
+        _cmp(f"comm/exchange/{it}", vals[0], want, 1e-6)
+        assert torch.equal(comms[0].grad, comms[1].grad)                 # both ranks hold the same sum
+        gsum = grads[0].double() + grads[1].double()
+        _cmp(f"comm/sum/{it}", comms[0].grad, gsum, 1e-6)
+        opt.zero_grad()
+        ref_p.grad = 0.5 * gsum
+        opt.step()
+        assert torch.equal(ps[0], ps[1])
+        _cmp(f"comm/adam_p/{it}", ps[0], ref_p.detach(), 1e-5)
+        assert int(steps[0].item()) == it + 1

@@ -820,6 +820,10 @@ def main():
                     {"label": l, "launches_per_step": c, "avg_ms": a, "ms_per_step": s} for l, c, a, s in table]}, f,
                     indent=1)
 
+    comm_kind = None
+    if world > 1:
+        c = getattr(model._plan, "_comm", None)
+        comm_kind = c.kind if c is not None else "NCCL all-reduce (torch.distributed) captured in the step graph"
     value = world * B * args.steps / (ms * 1e-3)
     per_gpu = value / world
     whole = {"flops_per_window": FLOPS_PER_WINDOW_TRAIN, "bytes_per_window": BYTES_PER_WINDOW_TRAIN,
@@ -871,7 +875,7 @@ def main():
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bytes_in,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-            "clocks": clocks, "final_loss": final_loss, "cuda_graph": args.graph == "on",
+            "clocks": clocks, "final_loss": final_loss, "cuda_graph": args.graph == "on", "exchange": comm_kind,
             "roofline": roofline, "whole_step": whole, "cpu_baseline": cpu_base,
         }
         line.update(extras)

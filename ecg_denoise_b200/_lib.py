@@ -104,6 +104,13 @@ def load():
     for name in ("ralenet_adam", "ralenet_adam_dev"):
         getattr(lib, name).argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64] + [ctypes.c_float] * 4 + [
             ctypes.c_int32 if name == "ralenet_adam" else ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p]
+    P, I = ctypes.c_void_p, ctypes.c_int32
+    lib.ralenet_linear_fwd.argtypes = [P, P, P, P, I, I, I, P]
+    lib.ralenet_linear_bwd_data.argtypes = [P, P, P, I, I, I, P]
+    lib.ralenet_pe_add.argtypes = [P, P, P, I, I, P]
+    lib.ralenet_pconv1.argtypes = [P, P, P, I, I, I, I, P]
+    lib.ralenet_pconv1_wgrad.argtypes = [P, P, P, I, I, I, P]
+    lib.ralenet_wgrad.argtypes = [P, I, P, I, I, I, I, P, P, P]
     lib.ralenet_comm_bytes.restype = ctypes.c_uint64
     lib.ralenet_comm_bytes.argtypes = [ctypes.c_uint64]
     lib.ralenet_comm_exchange.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32,

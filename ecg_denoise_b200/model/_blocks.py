@@ -41,7 +41,17 @@ class PartialConv_1d(nn.Module):
             _unsupported(f"PartialConv_1d with {self.dim_conv3} convolved channels")
 
     def forward(self, x):
-        _unsupported("stand-alone PartialConv_1d.forward (fused into Mlp.forward)")
+        """stand-alone use on a channels-first (B, dim, L) tensor (reference forward_split_cat :54-59 /
+        forward_slicing :47-52 -- same arithmetic); inside Mlp.forward the conv is fused into the feed-forward kernel."""
+        return ops.PartialConvFn.apply(x, self.partial_conv3.weight)
+
+
+def drop_path(x, drop_prob: float = 0., training: bool = False, scale_by_keep: bool = True):
+    """reference model/transformer.py:62-79.  Stochastic depth is never enabled on the RA-LENet path (every block is
+    built with drop_path = 0 -> nn.Identity, :367), so only the pass-through cases exist here."""
+    if drop_prob == 0. or not training:
+        return x
+    _unsupported("stochastic depth (drop_path > 0 in training mode)")
 
 
 class DropPath(nn.Module):
@@ -134,7 +144,9 @@ class AbsPositionalEncoding(nn.Module):
         self.P[:, :, 1::2] = torch.cos(pos / freq)
 
     def forward(self, X):
-        _unsupported("stand-alone AbsPositionalEncoding.forward (fused into TransformerBlock.forward)")
+        """X + P[:, :L] (reference :179-181).  Inside TransformerBlock.forward this is fused into the attention
+        kernel together with the sqrt(C) scale and LayerNorm."""
+        return ops.PeAddFn.apply(X)
 
 
 class LinearProjection(nn.Module):
@@ -151,7 +163,17 @@ class LinearProjection(nn.Module):
             _unsupported("dropout > 0")
 
     def forward(self, x, attn_kv=None):
-        _unsupported("stand-alone LinearProjection.forward (fused into MSAttention.forward)")
+        """(q, k, v), each (B, heads, L, head_dim) (reference :226-247).  Inside MSAttention.forward the projections
+        are fused into the attention kernel."""
+        if attn_kv is not None:
+            _unsupported("cross attention (attn_kv)")
+        B_, N, C = x.shape
+        hd = self.inner_dim // self.heads
+        q = ops.LinearFn.apply(x, self.to_q.weight, self.to_q.bias)
+        kv = ops.LinearFn.apply(x, self.to_kv.weight, self.to_kv.bias)
+        q = q.reshape(B_, N, 1, self.heads, hd).permute(2, 0, 3, 1, 4)[0]
+        kv = kv.reshape(B_, N, 2, self.heads, hd).permute(2, 0, 3, 1, 4)
+        return q, kv[0], kv[1]
 
 
 class MSAttention(nn.Module):

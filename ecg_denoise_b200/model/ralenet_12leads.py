@@ -12,7 +12,7 @@ import torch.nn as nn
 from .. import ops
 from ._blocks import (eca_layer_1d, AbsPositionalEncoding, BasicLayer, DropPath, LinearProjection, Mlp, MSAttention,  # noqa: F401
                       PartialConv_1d, PatchMerging, PatchSeparate, RelativePositionEmbedding, TransformerBlock,
-                      _RalenetBase, build_ralenet, mask_fill)
+                      _RalenetBase, build_ralenet, drop_path, mask_fill)
 
 
 class ralenet(_RalenetBase):

@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from . import _blocks as _b
 from ._blocks import (eca_layer_1d, AbsPositionalEncoding, DropPath, LinearProjection, MSAttention, PartialConv_1d,  # noqa: F401
-                      PatchMerging, PatchSeparate, _RalenetBase, build_ralenet)
+                      PatchMerging, PatchSeparate, _RalenetBase, build_ralenet, drop_path)
 
 
 class Mlp(_b.Mlp):

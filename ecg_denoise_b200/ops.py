@@ -362,6 +362,87 @@ def snr_mix(data: torch.Tensor, noise: torch.Tensor, snr_db) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# stand-alone forwards of the helper modules (small_ops.cu) -- fused away inside ralenet.forward, kept callable
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b over the last dimension (the nn.Linear inside LinearProjection.forward,
+    model/transformer.py:243-244, called on its own)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = _chk(x, "x")
+        K, N = x.shape[-1], w.shape[0]
+        M = x.numel() // K
+        y = torch.empty(*x.shape[:-1], N, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().ralenet_linear_fwd(x.data_ptr(), w.data_ptr(), _p(b), y.data_ptr(), M, K, N, _stream()))
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _chk(dy, "grad")
+        K, N = x.shape[-1], w.shape[0]
+        M = x.numel() // K
+        lib = _lib.load()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _lib.check(lib.ralenet_linear_bwd_data(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), M, K, N, _stream()))
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.zeros_like(w)
+            db = torch.zeros(N, device=x.device, dtype=torch.float32) if ctx.has_bias else None
+            _lib.check(lib.ralenet_wgrad(dy.data_ptr(), N, x.data_ptr(), K, M, N, K, dw.data_ptr(), _p(db), _stream()))
+        return dx, dw, db
+
+
+class PeAddFn(torch.autograd.Function):
+    """AbsPositionalEncoding.forward (model/transformer.py:179-181): X + P[:, :L] (dropout p = 0)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk(x, "x")
+        B, L, C = x.shape
+        y = torch.empty_like(x)
+        _lib.check(_lib.load().ralenet_pe_add(x.data_ptr(), pos_table(L, C, x.device).data_ptr(), y.data_ptr(), B,
+                                              L * C, _stream()))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy
+
+
+class PartialConvFn(torch.autograd.Function):
+    """PartialConv_1d.forward_split_cat (model/transformer.py:54-59) with dim_conv3 == 1 on a channels-first
+    (B, C, L) tensor: channel 0 <- Conv1d(1, 1, 3, padding 1, bias=False), channels 1.. pass through."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x = _chk(x, "x")
+        B, C, L = x.shape
+        y = torch.empty_like(x)
+        _lib.check(_lib.load().ralenet_pconv1(x.data_ptr(), w.data_ptr(), y.data_ptr(), B, C, L, 0, _stream()))
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _chk(dy, "grad")
+        B, C, L = x.shape
+        lib = _lib.load()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _lib.check(lib.ralenet_pconv1(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), B, C, L, 1, _stream()))
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros_like(w)
+            _lib.check(lib.ralenet_pconv1_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), B, C, L, _stream()))
+        return dx, dw
+
+
 def mse_loss_metrics(pred: torch.Tensor, target: torch.Tensor, want_grad: bool = True, gscale: float = 1.0,
                      global_numel: Optional[int] = None, weight: Optional[torch.Tensor] = None):
     """Fused F.mse_loss (denoise_train.py:53) + its gradient + per-window RMSE / SNR

@@ -402,6 +402,24 @@ int ralenet_comm_exchange(const rl_comm* c, int32_t set, float* vals, int32_t n,
 int ralenet_comm_allreduce_adam(const rl_comm* c, float* p, float* m, float* v, float lr, float beta1, float beta2,
                                 float eps, int32_t* step_dev, float gscale, int32_t grid, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone forwards of helper modules that ralenet.forward fuses away (small_ops.cu; NOT on the hot path):
+ *   ralenet_linear_fwd       y[M,N] = x[M,K] w[N,K]^T (+ b[N])     nn.Linear inside LinearProjection.forward
+ *                            (model/transformer.py:226-247: to_q, to_kv) called on its own
+ *   ralenet_linear_bwd_data  dx[M,K] = dy[M,N] w[N,K]              (weight gradient: ralenet_wgrad)
+ *   ralenet_pe_add           y = x + P[:L]  broadcast over the batch, per = L*C   AbsPositionalEncoding.forward (:179-181)
+ *   ralenet_pconv1           PartialConv_1d.forward_split_cat (:54-59) with one convolved channel: channels-first
+ *                            [B,C,L], channel 0 <- Conv1d(1,1,3,pad 1,no bias), channels 1.. copied; transpose = 1
+ *                            gives the data gradient;  ralenet_pconv1_wgrad: dw[3] += the weight gradient
+ * ------------------------------------------------------------------------------------------ */
+int ralenet_linear_fwd(const float* x, const float* w, const float* b, float* y, int32_t M, int32_t K, int32_t N,
+                       void* stream);
+int ralenet_linear_bwd_data(const float* dy, const float* w, float* dx, int32_t M, int32_t K, int32_t N, void* stream);
+int ralenet_pe_add(const float* x, const float* pe, float* y, int32_t B, int32_t per, void* stream);
+int ralenet_pconv1(const float* x, const float* w, float* y, int32_t B, int32_t C, int32_t L, int32_t transpose,
+                   void* stream);
+int ralenet_pconv1_wgrad(const float* dy, const float* x, float* dw, int32_t B, int32_t C, int32_t L, void* stream);
+
 /* Per-launch timing for bench.py's roofline pass: after ralenet_profile_begin(stream) every kernel this
  * library launches is followed by a CUDA event on `stream`; ralenet_profile_end() waits for the last one and
  * returns the number of launches, their labels ("kernel<C>", label_stride bytes each) and durations in ms.

@@ -632,3 +632,56 @@ def test_comm_kernels_two_ranks_on_one_gpu():
         assert torch.equal(ps[0], ps[1])
         _cmp(f"comm/adam_p/{it}", ps[0], ref_p.detach(), 1e-5)
         assert int(steps[0].item()) == it + 1
+
+
+def test_standalone_helper_module_forwards():
+    """LinearProjection.forward, AbsPositionalEncoding.forward, PartialConv_1d.forward and drop_path() called on their
+    own, as the reference's modules allow (model/transformer.py:226-247, 179-181, 54-59, 62-79): same values and
+    gradients as the plain formulas in float64."""
+    from ecg_denoise_b200.model import transformer as T
+    rs = np.random.RandomState(77)
+    B, L, C, H = 3, 64, 32, 8
+    lp = T.LinearProjection(C, H, 4).cuda()
+    x = _rand(rs, B, L, C)
+    xt = _dev(x)
+    q, k, v = lp(xt)
+    wq, bq = lp.to_q.weight.detach().double().cpu(), lp.to_q.bias.detach().double().cpu()
+    wkv, bkv = lp.to_kv.weight.detach().double().cpu(), lp.to_kv.bias.detach().double().cpu()
+    q_ref = (x @ wq.t() + bq).reshape(B, L, H, 4).permute(0, 2, 1, 3)
+    kv_ref = (x @ wkv.t() + bkv).reshape(B, L, 2, H, 4).permute(2, 0, 3, 1, 4)
+    _cmp("standalone/linproj/q", q, q_ref)
+    _cmp("standalone/linproj/k", k, kv_ref[0])
+    _cmp("standalone/linproj/v", v, kv_ref[1])
+    gq, gk, gv = _rand(rs, B, H, L, 4), _rand(rs, B, H, L, 4), _rand(rs, B, H, L, 4)
+    (q * gq.float().cuda()).sum().add((k * gk.float().cuda()).sum()).add((v * gv.float().cuda()).sum()).backward()
+    dq2 = gq.permute(0, 2, 1, 3).reshape(B * L, C)
+    dkv2 = torch.stack([gk, gv]).permute(1, 3, 0, 2, 4).reshape(B * L, 2 * C)
+    _cmp("standalone/linproj/dx", xt.grad, (dq2 @ wq + dkv2 @ wkv).reshape(B, L, C))
+    _cmp("standalone/linproj/d_wq", lp.to_q.weight.grad, dq2.t() @ x.reshape(-1, C))
+    _cmp("standalone/linproj/d_bkv", lp.to_kv.bias.grad, dkv2.sum(0))
+    # AbsPositionalEncoding
+    pe = T.AbsPositionalEncoding(C)
+    y = pe(_dev(x, False))
+    _cmp("standalone/abs_pe", y, x + pe.P[0, :L].double(), 1e-6)
+    # PartialConv_1d on a channels-first tensor
+    pc = T.PartialConv_1d(4 * C, 4 * C, "split_cat").cuda()
+    xc = _rand(rs, B, 4 * C, L)
+    xct = _dev(xc)
+    yc = pc(xct)
+    w = pc.partial_conv3.weight.detach().double().cpu()
+    ref = xc.clone()
+    ref[:, :1] = torch.nn.functional.conv1d(xc[:, :1], w, padding=1)
+    _cmp("standalone/pconv/y", yc, ref, 1e-5)
+    g = _rand(rs, B, 4 * C, L)
+    yc.backward(g.float().cuda())
+    xr = xc.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    yr = torch.cat([torch.nn.functional.conv1d(xr[:, :1], wr, padding=1), xr[:, 1:]], 1)
+    yr.backward(g)
+    _cmp("standalone/pconv/dx", xct.grad, xr.grad, 1e-5)
+    _cmp("standalone/pconv/dw", pc.partial_conv3.weight.grad, wr.grad, 1e-5)
+    # drop_path: identity whenever the reference's would be
+    t = torch.ones(2, 3, device="cuda")
+    assert T.drop_path(t, 0.0, True) is t and T.drop_path(t, 0.3, False) is t
+    with pytest.raises(NotImplementedError):
+        T.drop_path(t, 0.3, True)

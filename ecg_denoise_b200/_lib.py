@@ -111,6 +111,7 @@ def load():
     lib.ralenet_pconv1.argtypes = [P, P, P, I, I, I, I, P]
     lib.ralenet_pconv1_wgrad.argtypes = [P, P, P, I, I, I, P]
     lib.ralenet_wgrad.argtypes = [P, I, P, I, I, I, I, P, P, P]
+    lib.ralenet_synth_windows.argtypes = [P, P, I, I, I, ctypes.c_uint64, P, I, P]
     lib.ralenet_comm_bytes.restype = ctypes.c_uint64
     lib.ralenet_comm_bytes.argtypes = [ctypes.c_uint64]
     lib.ralenet_comm_exchange.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32,

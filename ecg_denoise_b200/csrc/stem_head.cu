@@ -617,6 +617,11 @@ extern "C" int ralenet_mse(const rl_mse_args* a, void* stream) {
   return rl_check_launch("mse_kernel");
 }
 
+// tensor-core implicit-GEMM path for the k = 13 layers of newrale (conv_mma.cu)
+bool rl_conv13_eligible(int L, int Ci, int Co, int K);
+int rl_conv13_fwd_mma(const rl_conv_fwd_args* a, cudaStream_t st);
+int rl_conv13_bwd_mma(const rl_conv_bwd_args* a, cudaStream_t st);
+
 static int conv_check(int B, int L, int Ci, int Co, int K, size_t* smem, bool bwd) {
   RL_REQUIRE(B > 0 && L > 0 && L <= 8192 && Ci > 0 && Co > 0 && Ci <= CONV_MAX_CI && Co <= CONV_MAX_CI && K % 2 == 1 &&
                  K <= CONV_MAX_K,
@@ -632,6 +637,7 @@ extern "C" int ralenet_conv1d_fwd(const rl_conv_fwd_args* a, void* stream) {
   size_t smem = 0;
   if (int rc = conv_check(a->B, a->L, a->Cin, a->Cout, a->K, &smem, false)) return rc;
   RL_REQUIRE(a->x && a->w && a->y, RL_ERR_NULL, "conv1d_fwd: NULL tensor");
+  if (rl_conv13_eligible(a->L, a->Cin, a->Cout, a->K)) return rl_conv13_fwd_mma(a, (cudaStream_t)stream);
   if (int rc = rl_set_smem(conv1d_fwd_kernel, smem)) return rc;
   rl_prof_pre((cudaStream_t)stream);
   conv1d_fwd_kernel<<<a->B, RL_NT, smem, (cudaStream_t)stream>>>(*a);
@@ -643,6 +649,7 @@ extern "C" int ralenet_conv1d_bwd(const rl_conv_bwd_args* a, void* stream) {
   size_t smem = 0;
   if (int rc = conv_check(a->B, a->L, a->Cin, a->Cout, a->K, &smem, true)) return rc;
   RL_REQUIRE(a->dy && a->x && a->w, RL_ERR_NULL, "conv1d_bwd: NULL tensor");
+  if (rl_conv13_eligible(a->L, a->Cin, a->Cout, a->K)) return rl_conv13_bwd_mma(a, (cudaStream_t)stream);
   if (int rc = rl_set_smem(conv1d_bwd_kernel, smem)) return rc;
   rl_prof_pre((cudaStream_t)stream);
   conv1d_bwd_kernel<<<a->B, RL_NT, smem, (cudaStream_t)stream>>>(*a);

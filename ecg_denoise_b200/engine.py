@@ -378,6 +378,7 @@ class FusedTrainer:
         # RALENET_COMM=nccl keeps the three torch.distributed all-reduces (the round-1 path, kept for A/B)
         self.comm = None
         self.comm_mode = os.environ.get("RALENET_COMM", "symm")
+        self._synth = None            # synth_device.DeviceSynth feeding the step (step_synth)
 
     def _allreduce(self, t: torch.Tensor):
         torch.distributed.all_reduce(t, group=self.pg)
@@ -433,6 +434,8 @@ class FusedTrainer:
 
         def seg_a():
             self.net.train()
+            if self._synth is not None:       # draw this step's batch on the device (batch index = Adam step counter)
+                self._synth.fill(x, target, self.step_dev)
             plan.flat_grad.zero_()
             _call("ralenet_net_fwd_stats", ctypes.byref(cfg()), ctypes.byref(plan.P), xp, st())
 
@@ -568,6 +571,7 @@ class FusedTrainer:
         out) as device tensors (no host sync)."""
         x, target = _chk(x, "x"), _chk(target, "target")
         self._prepare(x.shape, x.device)
+        self._set_synth(None)
         if not self.use_graph:
             return self._step_impl(x, target)
         sx, st_ = self._static
@@ -575,11 +579,26 @@ class FusedTrainer:
         st_.copy_(target, non_blocking=True)
         return self._replay()
 
+    def _set_synth(self, synth):
+        if self._synth is not synth:
+            self._synth = synth
+            self.graph = None             # the captured step changes
+
+    def step_synth(self, synth):
+        """one training step on a batch drawn ON THE DEVICE by `synth` (synth_device.DeviceSynth): no host traffic at
+        all; with use_graph the generator is part of the step's CUDA graph and every replay sees new windows.
+        Returns (loss[1], rmse[B], snr[B], out) like step()."""
+        self._prepare((synth.B, synth.leads, synth.L), synth.device)
+        self._set_synth(synth)
+        sx, st_ = self._static
+        return self._replay() if self.use_graph else self._step_impl(sx, st_)
+
     def step_host(self, hx: torch.Tensor, ht: torch.Tensor) -> torch.Tensor:
         """one training step from (pinned) HOST tensors: async H2D of the batch into the static device buffers,
         then the step; returns the device loss tensor (the caller's .item() is the D2H read)."""
         dev = next(self.net.parameters()).device
         self._prepare(hx.shape, dev)
+        self._set_synth(None)
         sx, st_ = self._static
         sx.copy_(hx, non_blocking=True)
         st_.copy_(ht, non_blocking=True)

@@ -268,6 +268,9 @@ typedef struct {
 } rl_conv_bwd_args;
 int ralenet_conv1d_fwd(const rl_conv_fwd_args* a, void* stream);
 int ralenet_conv1d_bwd(const rl_conv_bwd_args* a, void* stream);
+/* k = 13 layers: 1 (default) = implicit-GEMM tensor-core kernels (conv_mma.cu), 0 = scalar FMA kernels (stem_head.cu).
+ * Same function; A/B switch, initial value from RALENET_CONV_MMA.  Returns the previous setting. */
+int ralenet_set_conv_mma(int on);
 
 /* ------------------------------------------------------------------------------------------
  * Flat multi-tensor Adam: torch.optim.Adam(lr=1e-3) defaults (denoise_train.py:24, 57) over one
@@ -365,6 +368,15 @@ int ralenet_eca_bwd(const rl_eca_bwd_args* a, void* stream);
  * with the means over all `per` elements (leads x samples) of window b.  data, noise, out: [B][per]; snr_db: [B]. */
 int ralenet_snr_mix(const float* data, const float* noise, const float* snr_db, float* out, int32_t B, int32_t per,
                     void* stream);
+
+/* Device-side training-batch synthesiser (synth.cu): MIT-BIH-style windows generated on
+ * the GPU -- beat trains of P-QRS-T Gaussians (R peak of the middle beat at L/2 +- 8), per-lead z-normalisation
+ * (np_norm, local_utils/local_utils.py:261-266), and bw / ma / em style noise (kind 0 / 1 / 2, 3 = all three, the
+ * reference's `emb`) with zero mean; mix with ralenet_snr_mix for the reference's SNR-targeted pairs
+ * (local_utils.py:176-192).  clean, noise: [B][leads][L], L <= 1024.  The random stream is a pure function of
+ * (seed, *counter_dev, window, lead, sample); counter_dev (device int32, e.g. the Adam step counter) may be NULL. */
+int ralenet_synth_windows(float* clean, float* noise, int32_t B, int32_t leads, int32_t L, uint64_t seed,
+                          const int32_t* counter_dev, int32_t kind, void* stream);
 
 /* Weight-gradient GEMM over the token dimension (used by every *_bwd above; exported for benchmarks):
  *   dW[n*K + k] += sum_m dY[m*ldy + n] * X[m*ldx + k],   db[n] += sum_m dY[m*ldy + n]   (db may be NULL) */

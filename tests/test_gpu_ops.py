@@ -363,10 +363,22 @@ def test_head(ops):
         _cmp(f"head/d_{k}", d[k].grad, gr[k])
 
 
+@pytest.mark.parametrize("mma", [1, 0])
 @pytest.mark.parametrize("ci,co,act", [(12, 6, True), (6, 2, True), (2, 6, True), (6, 12, False)])
-def test_conv13(ops, ci, co, act):
+def test_conv13(ops, ci, co, act, mma):
+    """the four lead-mixing convolutions of newrale: implicit-GEMM tensor-core kernels (conv_mma.cu, mma = 1) and the
+    scalar kernels (stem_head.cu, mma = 0), both against the fp64 oracle, at a ragged batch."""
+    from ecg_denoise_b200 import _lib
+    prev = _lib.load().ralenet_set_conv_mma(mma)
+    try:
+        _conv13_case(ops, ci, co, act, f"{'mma' if mma else 'fma'}")
+    finally:
+        _lib.load().ralenet_set_conv_mma(prev)
+
+
+def _conv13_case(ops, ci, co, act, kind):
     rs = np.random.RandomState(700 + ci)
-    B, L = 3, 256
+    B, L = 37, 256
     w, b = _rand(rs, co, ci, 13, scale=(13 * ci) ** -0.5), 0.1 * _rand(rs, co)
     x, dy = _rand(rs, B, ci, L), _rand(rs, B, co, L)
     c = O.conv1d_fwd(x, w, b)
@@ -375,7 +387,7 @@ def test_conv13(ops, ci, co, act):
     dx_ref, dw_ref, db_ref = O.conv1d_bwd(dc, x, w)
     xt, wt, bt = _dev(x), _dev(w), _dev(b)
     y = ops.Conv1dFn.apply(xt, wt, bt, act, 0.01)
-    tag = f"conv13/{ci}to{co}"
+    tag = f"conv13/{kind}/{ci}to{co}"
     _cmp(tag + "/y", y, y_ref)
     y.backward(dy.float().cuda())
     _cmp(tag + "/dx", xt.grad, dx_ref)
@@ -685,3 +697,63 @@ def test_standalone_helper_module_forwards():
     assert T.drop_path(t, 0.0, True) is t and T.drop_path(t, 0.3, False) is t
     with pytest.raises(NotImplementedError):
         T.drop_path(t, 0.3, True)
+
+
+@pytest.mark.parametrize("kind", ["bw", "ma", "em", "emb"])
+def test_device_synth_batch_properties(kind):
+    """device-side batch synthesiser (synth.cu + snr_mix): z-normalised clean leads (np_norm), R peak of the middle
+    beat at L/2 +- 8, zero-mean noise, the mixed window has exactly the requested SNR (single_snr_noise_add's
+    definition, local_utils/local_utils.py:176-192), deterministic in (seed, counter), new windows per counter."""
+    from ecg_denoise_b200.synth_device import DeviceSynth
+    B, L = 64, 256
+    sy = DeviceSynth(B, 2, L, seed=7, kind=kind, snr_db=-4.0)
+    ctr = torch.zeros(1, device="cuda", dtype=torch.int32)
+    noisy, clean = sy.batch(ctr)
+    noisy2, clean2 = sy.batch(ctr)
+    assert torch.equal(noisy, noisy2) and torch.equal(clean, clean2)
+    ctr += 1
+    noisy3, clean3 = sy.batch(ctr)
+    assert not torch.equal(clean, clean3)
+    c = clean.double().cpu()
+    assert torch.isfinite(noisy).all() and torch.isfinite(clean).all()
+    assert float(c.mean(-1).abs().max()) < 1e-4
+    assert float((c.std(-1, unbiased=False) - 1).abs().max()) < 1e-3
+    lead0 = c[:, 0]
+    centre = lead0[:, L // 2 - 9:L // 2 + 10].max(-1).values
+    assert bool((centre >= 0.7 * lead0.max(-1).values).all())          # an R wave sits at the window centre
+    n = (noisy.double().cpu() - c).reshape(B, -1)
+    assert float(n.reshape(B, 2, L).mean(-1).abs().max()) < 1e-3 * float(n.abs().max())
+    snr = 10 * torch.log10((c.reshape(B, -1) ** 2).mean(1) / (n ** 2).mean(1))
+    assert float((snr + 4.0).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_trainer_step_synth(graph):
+    """FusedTrainer.step_synth: the generator runs inside the step (inside its CUDA graph when use_graph), each step
+    sees the batch of its own Adam step index, and the result equals step() on that same batch."""
+    from ecg_denoise_b200.engine import FusedTrainer
+    from ecg_denoise_b200.model import transformer
+    from ecg_denoise_b200.synth_device import DeviceSynth
+    from oracle import synth_weights as SW
+    sd = SW.make_state_dict("rw", 1, 9)
+    B = 16
+    sy = DeviceSynth(B, 2, 256, seed=3, kind="emb", snr_db=0.0)
+
+    def fresh():
+        m = transformer.ralenet(high_level_enhence=True)
+        m.load_state_dict(sd)
+        return m.cuda()
+
+    ma, mb = fresh(), fresh()
+    ta, tb = FusedTrainer(ma, use_graph=graph), FusedTrainer(mb, use_graph=False)
+    ctr = torch.zeros(1, device="cuda", dtype=torch.int32)
+    for it in range(3):
+        la = ta.step_synth(sy)[0].item()
+        x, t = sy.batch(ctr)                    # the batch step `it` must have drawn (counter = steps done so far)
+        lb = tb.step(x, t)[0].item()
+        ctr += 1
+        assert abs(la - lb) <= 1e-5 * abs(lb), (it, la, lb)
+    for (n, p), (_, q) in zip(ma.named_parameters(), mb.named_parameters()):
+        if n.endswith("to_kv.bias"):
+            continue
+        _cmp(f"step_synth/graph{int(graph)}/{n}", p.detach(), q.detach(), 1e-4)

@@ -490,9 +490,35 @@ def train12_record(dev, world, rank, steps, warmup):
     barrier()
     ms_e2e = 1e3 * (time.perf_counter() - t0)
     ms, ms_e2e = max_over_ranks([ms, ms_e2e], dev, world)
+    fused = None
+    if world == 1:
+        # the same step through engine.FineTuneTrainer: C ABI calls on static buffers, flat Adam, ONE CUDA graph
+        from ecg_denoise_b200.engine import FineTuneTrainer
+        ft = FineTuneTrainer(model, lr=1e-3, use_graph=True)
+        for _ in range(warmup):
+            ft.step(dx, dt)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(steps):
+            ft.step(dx, dt)
+        f1.record()
+        torch.cuda.synchronize()
+        fms = f0.elapsed_time(f1)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fl = ft.step_host(hx, ht).item()
+        fms_e2e = 1e3 * (time.perf_counter() - t0)
+        fused = {"value": B * steps / (fms * 1e-3), "unit": "12-lead windows/s", "ms_per_step": fms / steps,
+                 "e2e": {"value": B * steps / (fms_e2e * 1e-3), "unit": "12-lead windows/s",
+                         "h2d_bytes_per_step": 2 * B * 12 * 256 * 4, "d2h_bytes_per_step": 4},
+                 "final_loss": float(fl),
+                 "what": "engine.FineTuneTrainer: the same kernels through the C ABI on static buffers, flat Adam, "
+                         "whole step replayed from one CUDA graph"}
+        ft.close()
     return {"metric": "RA-LENet 12-lead fine-tune step throughput (fwd+bwd+Adam, frozen core)",
             "value": world * B * steps / (ms * 1e-3), "unit": "12-lead windows/s", "ms_per_step": ms / steps,
-            "steps": steps, "scaling": "weak",
+            "steps": steps, "scaling": "weak", "fused_graph": fused,
             "workload": f"configs[2]: newrale(ralenet(high_level_enhence=True)), {R} records x 12 x {T} per GPU "
                         f"-> {B} windows of 12 x 256 per step (reference-native shape, SURVEY F2), MSE, "
                         "torch.optim.Adam lr 1e-3 on the 4 Conv1d k13 layers, core frozen",

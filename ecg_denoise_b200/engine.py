@@ -357,10 +357,14 @@ class FusedTrainer:
     """
 
     def __init__(self, net: nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 process_group=None, use_graph: bool = False, graph_collectives: Optional[bool] = None):
+                 process_group=None, use_graph: bool = False, graph_collectives: Optional[bool] = None,
+                 loss_weight: Optional[torch.Tensor] = None):
         from . import ops
         self.ops = ops
         self.net = net
+        # optional R-wave-weighted reconstruction loss (north-star extension; the reference's loss is plain MSE,
+        # SURVEY F4): loss = mean(w * (pred - target)^2), w over the flattened (lead, sample) axis; None = F.mse_loss
+        self.loss_weight = loss_weight
         self.plan: NetPlan = net._plan
         self.lr, self.betas, self.eps = lr, betas, eps
         self.pg = process_group
@@ -442,7 +446,8 @@ class FusedTrainer:
         def seg_b():
             c = cfg()
             _call("ralenet_net_fwd", ctypes.byref(c), ctypes.byref(plan.P), xp, ctypes.c_void_p(out.data_ptr()), st())
-            loss, dout, rmse, snr = ops.mse_loss_metrics(out, target, True, 1.0, out.numel() * self.world)
+            loss, dout, rmse, snr = ops.mse_loss_metrics(out, target, True, 1.0, out.numel() * self.world,
+                                                         weight=self.loss_weight)
             _call("ralenet_net_bwd", ctypes.byref(c), ctypes.byref(plan.P), ctypes.byref(plan.G), xp,
                   ctypes.c_void_p(dout.data_ptr()), st())
             self._res = (loss, rmse, snr, out)
@@ -603,3 +608,149 @@ class FusedTrainer:
         sx.copy_(hx, non_blocking=True)
         st_.copy_(ht, non_blocking=True)
         return (self._replay() if self.use_graph else self._step_impl(sx, st_))[0]
+
+
+class FineTuneTrainer:
+    """The fast path of the 12-lead fine-tuning step (Transfer_learning.py:71-82 driving denoise_train.py:51-57):
+    `newrale` = Conv1d(12->6,k13) -> Conv1d(6->2,k13) -> frozen RA-LENet core -> Conv1d(2->6,k13) -> Conv1d(6->12,k13)
+    (model/ralenet_12leads.py:680-709), MSE, Adam(lr 1e-3) on the 2,210 parameters of the four convolutions.
+    Same kernels as the drop-in module path (ops.Conv1dFn, RalenetFn), but enqueued straight through the C ABI on
+    pre-allocated buffers -- no autograd graph, no per-tensor optimizer, one flat Adam -- so the whole step
+    (forward, loss + metrics, data gradients through the frozen core, conv weight gradients, Adam) replays from ONE
+    CUDA graph.  The core stays in whatever mode `model.rale.training` says (model.train() puts its BatchNorm in
+    batch-statistics mode and updates its running statistics, exactly like the reference's frozen core)."""
+
+    def __init__(self, model: nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 use_graph: bool = False):
+        from . import ops
+        self.ops, self.model, self.core = ops, model, model.rale
+        self.lr, self.betas, self.eps, self.use_graph = lr, betas, eps, use_graph
+        self.convs = [model.conv1, model.conv2, model.conv3, model.conv4]
+        self.slope = float(model.relu.negative_slope)
+        self.flat = None
+        self.graph = None
+        self._shape = None
+
+    def _setup(self, device):
+        plan: NetPlan = self.core._plan
+        plan.ensure(device)
+        plan.refresh_requires_grad()
+        ps = [p for c in self.convs for p in (c.weight, c.bias)]
+        if self.flat is not None and all(p.data_ptr() == self.flat.data_ptr() + 4 * o for p, o in zip(ps, self.offs)):
+            return
+        offs, n = [], 0
+        for p in ps:
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4
+        flat = torch.zeros(n, device=device, dtype=torch.float32)
+        grad = torch.zeros_like(flat)
+        with torch.no_grad():
+            for p, o in zip(ps, offs):
+                flat[o:o + p.numel()].copy_(p.detach().reshape(-1))
+                p.data = flat[o:o + p.numel()].view(p.shape)
+                p.grad = grad[o:o + p.numel()].view(p.shape)
+        self.flat, self.flat_grad, self.offs, self.ps = flat, grad, offs, ps
+        self.m, self.v = torch.zeros_like(flat), torch.zeros_like(flat)
+        self.step_dev = torch.zeros(1, device=device, dtype=torch.int32)
+        self.graph = None
+
+    def _prepare(self, shape, device):
+        self._setup(device)
+        if self._shape == tuple(shape):
+            return
+        B, Cin, L = shape
+        f = lambda c: torch.empty(B, c, L, device=device, dtype=torch.float32)
+        self._x, self._t = f(Cin), f(Cin)
+        self._a1, self._a2, self._r, self._a3, self._out = f(6), f(2), f(2), f(6), f(Cin)
+        self._da3, self._dr, self._da2, self._da1 = f(6), f(2), f(2), f(6)
+        self._ws = torch.empty(workspace_bytes(B, L, True), device=device, dtype=torch.uint8)
+        self._shape = tuple(shape)
+        self.graph = None
+
+    def _conv_fwd(self, x, conv, y, act):
+        Co, Ci, K = conv.weight.shape
+        a = _lib.STRUCTS["rl_conv_fwd_args"]()
+        a.B, a.L, a.Cin, a.Cout, a.K, a.act, a.slope = x.shape[0], x.shape[2], Ci, Co, K, int(act), self.slope
+        a.x, a.w, a.b, a.y = x.data_ptr(), conv.weight.data_ptr(), conv.bias.data_ptr(), y.data_ptr()
+        _lib.call("ralenet_conv1d_fwd", a, _stream())
+
+    def _conv_bwd(self, dy, x, conv, dx, act):
+        Co, Ci, K = conv.weight.shape
+        a = _lib.STRUCTS["rl_conv_bwd_args"]()
+        a.B, a.L, a.Cin, a.Cout, a.K, a.act, a.slope = x.shape[0], x.shape[2], Ci, Co, K, int(act), self.slope
+        a.dy, a.x, a.w, a.b = dy.data_ptr(), x.data_ptr(), conv.weight.data_ptr(), conv.bias.data_ptr()
+        a.dx = dx.data_ptr() if dx is not None else None
+        a.d_w, a.d_b = conv.weight.grad.data_ptr(), conv.bias.grad.data_ptr()
+        _lib.call("ralenet_conv1d_bwd", a, _stream())
+
+    def _step_impl(self):
+        plan: NetPlan = self.core._plan
+        c1, c2, c3, c4 = self.convs
+        B, _, L = self._x.shape
+        training = self.core.training
+        st = ctypes.c_void_p(_stream())
+        cfg = plan.cfg(B, L, training, True, self._ws)
+        a2p, rp = ctypes.c_void_p(self._a2.data_ptr()), ctypes.c_void_p(self._r.data_ptr())
+        self.flat_grad.zero_()
+        self._conv_fwd(self._x, c1, self._a1, True)
+        self._conv_fwd(self._a1, c2, self._a2, True)
+        if training:
+            _call("ralenet_net_fwd_stats", ctypes.byref(cfg), ctypes.byref(plan.P), a2p, st)
+        _call("ralenet_net_fwd", ctypes.byref(cfg), ctypes.byref(plan.P), a2p, rp, st)
+        self._conv_fwd(self._r, c3, self._a3, True)
+        self._conv_fwd(self._a3, c4, self._out, False)
+        loss, dout, rmse, snr = self.ops.mse_loss_metrics(self._out, self._t)
+        self._conv_bwd(dout, self._a3, c4, self._da3, False)
+        self._conv_bwd(self._da3, self._r, c3, self._dr, True)
+        _call("ralenet_net_bwd", ctypes.byref(cfg), ctypes.byref(plan.P), ctypes.byref(plan.G), a2p,
+              ctypes.c_void_p(self._dr.data_ptr()), st)
+        _call("ralenet_net_bwd_stem", ctypes.byref(cfg), ctypes.byref(plan.P), ctypes.byref(plan.G), a2p,
+              ctypes.c_void_p(self._da2.data_ptr()), st)
+        self._conv_bwd(self._da2, self._a1, c2, self._da1, True)
+        self._conv_bwd(self._da1, self._x, c1, None, True)
+        self.ops.adam_flat(self.flat, self.flat_grad, self.m, self.v, self.step_dev, self.lr, self.betas, self.eps, 1.0)
+        self._res = (loss, rmse, snr, self._out)
+        self._keep = dout
+        return self._res
+
+    def _run(self):
+        if not self.use_graph:
+            return self._step_impl()
+        if self.graph is None:
+            bn = self.core.conv1[2]
+            snap = (self.flat.clone(), self.m.clone(), self.v.clone(), self.step_dev.clone(), bn.running_mean.clone(),
+                    bn.running_var.clone(), bn.num_batches_tracked.clone())
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._step_impl()                         # warm-up (loads kernels, sizes the allocator pool)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.flat.copy_(snap[0]); self.m.copy_(snap[1]); self.v.copy_(snap[2]); self.step_dev.copy_(snap[3])
+            bn.running_mean.copy_(snap[4]); bn.running_var.copy_(snap[5]); bn.num_batches_tracked.copy_(snap[6])
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._step_impl()
+            self.graph, self._graph_out = g, self._res
+        self.graph.replay()
+        return self._graph_out
+
+    def step(self, x: torch.Tensor, target: torch.Tensor):
+        """one fine-tuning step on DEVICE tensors (B, 12, L).  Returns (loss[1], rmse[B], snr[B], out)."""
+        x, target = _chk(x, "x"), _chk(target, "target")
+        self._prepare(x.shape, x.device)
+        self._x.copy_(x, non_blocking=True)
+        self._t.copy_(target, non_blocking=True)
+        return self._run()
+
+    def step_host(self, hx: torch.Tensor, ht: torch.Tensor) -> torch.Tensor:
+        """the same from pinned HOST tensors (async H2D inside); returns the device loss tensor."""
+        dev = self.convs[0].weight.device
+        self._prepare(hx.shape, dev)
+        self._x.copy_(hx, non_blocking=True)
+        self._t.copy_(ht, non_blocking=True)
+        return self._run()[0]
+
+    def close(self):
+        self.graph = None
+        self._graph_out = None

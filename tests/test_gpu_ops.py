@@ -745,7 +745,9 @@ def test_fused_trainer_step_synth(graph):
         lb = tb.step(x, t)[0].item()
         ctr += 1
         assert abs(la - lb) <= 1e-5 * abs(lb), (it, la, lb)
+    # the two runs differ only by the summation order of the atomically accumulated weight gradients; Adam turns that
+    # noise into +-lr moves of elements whose gradient is ~0, so parameters are compared with that bound (3 steps x
+    # lr) and the gradients of the last step with the usual tolerance
+    _cmp(f"step_synth/graph{int(graph)}/flat_grad", ma._plan.flat_grad, mb._plan.flat_grad, RTOL)
     for (n, p), (_, q) in zip(ma.named_parameters(), mb.named_parameters()):
-        if n.endswith("to_kv.bias"):
-            continue
-        _cmp(f"step_synth/graph{int(graph)}/{n}", p.detach(), q.detach(), RTOL)    # 3 Adam steps apart
+        assert float((p.detach() - q.detach()).abs().max()) <= 3.2e-3, n

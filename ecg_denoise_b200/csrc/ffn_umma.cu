@@ -17,6 +17,7 @@
 #define RL_MINB 1
 #include "common.cuh"
 #include "umma.cuh"
+#include "tma.cuh"
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -39,26 +40,90 @@ struct FwdSmem {
 
 using umma::Ring;
 
-template <int C>
-__global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_ffn_fwd_args a) {
+// D[tmem] (+)= A[:, k0:k0+KC] * B^T with the 3-pass split; A: un-swizzled K-major tile pair (umma.cuh), B: one KC = 32
+// wide chunk in the K-major SWIZZLE_128B layout written by TMA (tma.cuh) and its remainder tile in the same layout
+__device__ __forceinline__ void mma_chunk_3x_tma(uint32_t tmem_d, const float* a_hi, const float* a_lo, int KT_A, int k0,
+                                                 const float* b_hi, const float* b_lo, uint32_t idesc, uint32_t accum) {
+  const uint32_t sbo_a = (uint32_t)(KT_A / 4) * 128u;
+  const uint32_t ah = umma::smem_u32(a_hi) + (uint32_t)(k0 / 4) * 128u, al = umma::smem_u32(a_lo) + (uint32_t)(k0 / 4) * 128u;
+  const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo);
+#pragma unroll
+  for (int ks = 0; ks < KC / 8; ++ks) {
+    const uint64_t dah = umma::make_desc(ah + ks * 256u, 128u, sbo_a), dal = umma::make_desc(al + ks * 256u, 128u, sbo_a);
+    const uint64_t dbh = tma::desc_sw128(bh + ks * 32u), dbl = tma::desc_sw128(bl + ks * 32u);
+    umma::mma_tf32(tmem_d, dal, dbh, idesc, accum);
+    umma::mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+    umma::mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+    accum = 1u;
+  }
+}
+
+// TMA = true: the weight chunks of fc1 and fc2 arrive through cp.async.bulk.tensor (tma.cuh) in one 2-stage ring that
+// runs across both GEMMs (chunks 0 .. C/32 - 1 from W1, then TS/32 chunks from W2); one thread issues, the CTA only
+// derives the tf32 remainder tile.  TMA = false: the round-1 path (registers -> st.shared), kept for A/B.
+template <int C, bool TMA>
+__global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_ffn_fwd_args a,
+                                                                      const __grid_constant__ CUtensorMap tm1,
+                                                                      const __grid_constant__ CUtensorMap tm2) {
   constexpr int L = 2048 / C, HC = 4 * C, NSL = HC / TS;
+  constexpr int NCH1 = C / KC, NCH2 = TS / KC;
   // the weights are not written by the preceding kernels of the step: pull the whole fc1 slice of this CTA into
   // registers before waiting on the programmatic dependency, so its L2 latency hides behind the previous kernel
-  umma::KStage<TS, KC, RL_NT> w1r[C / KC];
-  {
+  umma::KStage<TS, KC, RL_NT> w1r[TMA ? 1 : C / KC];
+  if constexpr (!TMA) {
     const float* w1s = a.w1 + (size_t)(blockIdx.x % NSL) * TS * C;
 #pragma unroll
     for (int j = 0; j < C / KC; ++j) w1r[j].load(w1s + j * KC, C, TS);
   }
-  extern __shared__ __align__(128) float smem[];
+  extern __shared__ __align__(1024) float smem[];
   float* sA_hi = smem;
   float* sA_lo = sA_hi + FwdSmem<C>::A_FLOATS;
   float* sB = sA_lo + FwdSmem<C>::A_FLOATS;                  // [2 stages][hi | lo][128 * KC]
   float* sg10 = sB + 4 * FwdSmem<C>::B_FLOATS;               // g1[:, 0] of the tile (slice 0)
   float* sfir = sg10 + TM;
   float* s_ln = sfir + TM;                                   // norm2 weight [C] | bias [C]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ln + 2 * C);   // 2 mbarriers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ln + 2 * C);   // [0,1]: MMAs of a ring buffer done; [2,3]: TMA landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  // chunk jj of the weight ring (tid 0): fc1 rows [128 r, 128 r + 128) x K chunk jj, then fc2 rows [0, C) x its
+  // K chunk inside hidden slice r
+  const int r_early = blockIdx.x % NSL;
+  auto tma_issue = [&](int jj) {
+    const int b = jj & 1;
+    float* dst = sB + b * 2 * FwdSmem<C>::B_FLOATS;
+    if (jj < NCH1) {
+      tma::expect_tx(bars + 2 + b, TS * KC * 4);
+      tma::load_2d(dst, &tm1, jj * KC, r_early * TS, bars + 2 + b);
+    } else {
+      tma::expect_tx(bars + 2 + b, C * KC * 4);
+      tma::load_2d(dst, &tm2, r_early * TS + (jj - NCH1) * KC, 0, bars + 2 + b);
+    }
+  };
+  // all threads: wait for chunk jj, derive its remainder tile (same swizzled layout, element-wise)
+  auto tma_consume = [&](int jj, int rows) {
+    const int b = jj & 1;
+    umma::mbar_wait(bars + 2 + b, (uint32_t)((jj >> 1) & 1));
+    const float4* hi4 = reinterpret_cast<const float4*>(sB + b * 2 * FwdSmem<C>::B_FLOATS);
+    float4* lo4 = reinterpret_cast<float4*>(sB + b * 2 * FwdSmem<C>::B_FLOATS + FwdSmem<C>::B_FLOATS);
+    for (int i = threadIdx.x; i < rows * KC / 4; i += RL_NT) {
+      const float4 v = hi4[i];
+      lo4[i] = make_float4(v.x - umma::trunc_tf32(v.x), v.y - umma::trunc_tf32(v.y), v.z - umma::trunc_tf32(v.z),
+                           v.w - umma::trunc_tf32(v.w));
+    }
+  };
+  if (threadIdx.x == 0) {
+    umma::mbar_init(bars, 1);
+    umma::mbar_init(bars + 1, 1);
+    umma::mbar_init(bars + 2, 1);
+    umma::mbar_init(bars + 3, 1);
+    umma::fence_mbar_init();
+    if constexpr (TMA) {
+      umma::fence_async_smem();
+      tma::prefetch_desc(&tm1);
+      tma::prefetch_desc(&tm2);
+      tma_issue(0);                      // weights are immutable inside the step: both ring buffers fill while the
+      tma_issue(1);                      // previous kernel drains
+    }
+  }
   // ... and so does the LayerNorm affine: staged in shared memory here, phase 1 then waits for one round of global
   // loads (x) instead of one more round per 16-byte chunk
   if ((a.flags & RL_F_PRENORM) && threadIdx.x < C / 2) {
@@ -79,11 +144,6 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
   const int nvalid = min(TM, a.B * L - (int)tok0);            // valid token rows of this tile
   const float* xw = a.x + tok0 * C;
 
-  if (tid == 0) {
-    umma::mbar_init(bars, 1);
-    umma::mbar_init(bars + 1, 1);
-    umma::fence_mbar_init();
-  }
   if (warp == 0) umma::tmem_alloc<TMEM_COLS>(tmem_slot);
   __syncthreads();                                           // staged LayerNorm affine visible to every warp
   RL_TS(umma, 2);
@@ -149,23 +209,34 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
     constexpr uint32_t idesc = umma::idesc_tf32(TM, TS);
 #pragma unroll
     for (int j = 0; j < C / KC; ++j) {
-      ring.wait_free();
       float* bh = sB + ring.buf() * 2 * FwdSmem<C>::B_FLOATS;
       float* bl = bh + FwdSmem<C>::B_FLOATS;
-      w1r[j].store(bh, bl);
+      if constexpr (TMA) {
+        tma_consume(j, TS);
+      } else {
+        ring.wait_free();
+        w1r[j].store(bh, bl);
+      }
       umma::fence_async_smem();
       __syncthreads();
       if (tid == 0) {
         umma::tc_fence_after();
-        umma::mma_chunk_3x<KC>(tb, sA_hi, sA_lo, C, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
+        if constexpr (TMA) mma_chunk_3x_tma(tb, sA_hi, sA_lo, C, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
+        else umma::mma_chunk_3x<KC>(tb, sA_hi, sA_lo, C, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
         umma::commit(bars + ring.buf());
+        if constexpr (TMA) {             // refill this buffer with chunk j + 2 as soon as its MMAs have drained
+          ++ring.chunk;
+          ring.wait_last();
+          --ring.chunk;
+          tma_issue(j + 2);              // (NCH2 >= 2: chunk j + 2 always exists here)
+        }
       }
       ++ring.chunk;
     }
   }
   // the fc2 slice of this CTA goes to registers now; its latency hides behind the epilogue below
-  umma::KStage<C, KC, RL_NT> w2r[TS / KC];
-  {
+  umma::KStage<C, KC, RL_NT> w2r[TMA ? 1 : TS / KC];
+  if constexpr (!TMA) {
     const float* w2s = a.w2 + (size_t)r * TS;
 #pragma unroll
     for (int j = 0; j < TS / KC; ++j) w2r[j].load(w2s + j * KC, HC, C);
@@ -243,16 +314,29 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
     constexpr uint32_t idesc = umma::idesc_tf32(TM, C);
 #pragma unroll
     for (int j = 0; j < TS / KC; ++j) {
-      ring.wait_free();
       float* bh = sB + ring.buf() * 2 * FwdSmem<C>::B_FLOATS;
       float* bl = bh + FwdSmem<C>::B_FLOATS;
-      w2r[j].store(bh, bl);
+      if constexpr (TMA) {
+        tma_consume(NCH1 + j, C);
+      } else {
+        ring.wait_free();
+        w2r[j].store(bh, bl);
+      }
       umma::fence_async_smem();
       __syncthreads();
       if (tid == 0) {
         umma::tc_fence_after();
-        umma::mma_chunk_3x<KC>(tb + TS, sA_hi, sA_lo, TS, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
+        if constexpr (TMA) mma_chunk_3x_tma(tb + TS, sA_hi, sA_lo, TS, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
+        else umma::mma_chunk_3x<KC>(tb + TS, sA_hi, sA_lo, TS, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
         umma::commit(bars + ring.buf());
+        if constexpr (TMA) {
+          if (j + 2 < TS / KC) {
+            ++ring.chunk;
+            ring.wait_last();
+            --ring.chunk;
+            tma_issue(NCH1 + j + 2);
+          }
+        }
       }
       ++ring.chunk;
     }
@@ -365,7 +449,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_umma_kernel(const rl_f
   }
   pdl_wait();
   pdl_trigger();
-  extern __shared__ __align__(128) float smem[];
+  extern __shared__ __align__(1024) float smem[];
   float* sA_hi = smem;
   float* sA_lo = sA_hi + BwdSmem<C>::A_FLOATS;
   float* sB = sA_lo + BwdSmem<C>::A_FLOATS;
@@ -662,13 +746,56 @@ int launch_cluster(void (*kernel)(const Args), size_t smem, int grid, int cl, co
 }  // namespace
 
 // returns 1 if the shape/mode is not handled here (caller falls through to the kernels in ffn_cluster.cu / ffn.cu)
+static int g_ffn_tma = -1;
+static int ffn_tma_on() {
+  if (g_ffn_tma < 0) {
+    const char* e = getenv("RALENET_UMMA_TMA");
+    g_ffn_tma = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_ffn_tma;
+}
+extern "C" int ralenet_set_umma_tma(int on) {
+  const int prev = ffn_tma_on();
+  g_ffn_tma = on ? 1 : 0;
+  return prev;
+}
+
+template <int C, bool TMA>
+static int launch_fwd(const rl_ffn_fwd_args* a, int tiles, cudaStream_t st) {
+  constexpr int NSL = 4 * C / TS;
+  CUtensorMap tm1 = {}, tm2 = {};
+  if (TMA) {
+    if (int rc = rl_tmap_weight(a->w1, 4 * C, C, C, TS, &tm1)) return rc;         // fc1 [4C][C]: 128-row slices
+    if (int rc = rl_tmap_weight(a->w2, C, 4 * C, 4 * C, C, &tm2)) return rc;      // fc2 [C][4C]: all C rows
+  }
+  auto kernel = ffn_fwd_umma_kernel<C, TMA>;
+  const size_t smem = FwdSmem<C>::BYTES + 64;
+  if (int rc = rl_set_smem(kernel, smem)) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles * NSL);
+  cfg.blockDim = dim3(RL_NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NSL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  rl_prof_pre(st);
+  cudaLaunchKernelEx(&cfg, kernel, *a, tm1, tm2);
+  return rl_check_launch("ffn_fwd_umma", C);
+}
+
 int rl_ffn_fwd_umma(const rl_ffn_fwd_args* a, cudaStream_t st) {
   if (a->L * a->C != 2048 || a->le_mode == RL_LE_DEPTHWISE) return 1;
   const int tiles = (a->B * a->L + TM - 1) / TM;
-  if (a->C == 128)
-    return launch_cluster(ffn_fwd_umma_kernel<128>, FwdSmem<128>::BYTES, tiles * 4, 4, *a, st, "ffn_fwd_umma", 128);
-  if (a->C == 64)
-    return launch_cluster(ffn_fwd_umma_kernel<64>, FwdSmem<64>::BYTES, tiles * 2, 2, *a, st, "ffn_fwd_umma", 64);
+  const bool tma_ok = ffn_tma_on() && ((uintptr_t)a->w1 % 16 == 0) && ((uintptr_t)a->w2 % 16 == 0);
+  if (a->C == 128) return tma_ok ? launch_fwd<128, true>(a, tiles, st) : launch_fwd<128, false>(a, tiles, st);
+  if (a->C == 64) return tma_ok ? launch_fwd<64, true>(a, tiles, st) : launch_fwd<64, false>(a, tiles, st);
   return 1;
 }
 

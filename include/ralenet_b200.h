@@ -108,6 +108,10 @@ int ralenet_set_attn_umma(int mode);
  * 1 (default) = tcgen05 kernels (wgrad_umma.cu), 0 = mma.sync kernels (wgrad.cu).  Same function; A/B switch,
  * initial value from RALENET_WGRAD_UMMA.  Returns the previous setting. */
 int ralenet_set_wgrad_umma(int on);
+/* Weight staging of the tcgen05 feed-forward forward kernels (C = 64, 128): 1 (default) = TMA (cp.async.bulk.tensor into
+ * the SWIZZLE_128B layout, tma.cuh), 0 = the round-1 path (ld.global -> registers -> st.shared).  Same function; A/B
+ * switch, initial value from RALENET_UMMA_TMA.  Returns the previous setting. */
+int ralenet_set_umma_tma(int on);
 
 /* ------------------------------------------------------------------------------------------
  * Feed-forward half:  y = x + fc2(GELU(leconv(GELU(fc1(LN2(x))))))  (+ extra)

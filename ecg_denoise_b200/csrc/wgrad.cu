@@ -214,7 +214,13 @@ int launch_group(WgGroup& g, int total_tiles, cudaStream_t st) {
 // problems are launched one by one on the FFMA kernel.
 int rl_launch_wgrad_group_umma(const RlWgradDesc* d, int n, int M, cudaStream_t st);   // wgrad_umma.cu
 
+int rl_launch_wgrad_group_reg(const RlWgradDesc* d, int n, int M, cudaStream_t st);    // wgrad_reg.cu
+
 int rl_launch_wgrad_group(const RlWgradDesc* d, int n, int M, cudaStream_t st) {
+  {
+    const int rc = rl_launch_wgrad_group_reg(d, n, M, st);     // register-tile kernel; 1: group not handled there
+    if (rc <= 0) return rc;
+  }
   {
     const int rc = rl_launch_wgrad_group_umma(d, n, M, st);    // tcgen05 kernels; 1: group not handled there
     if (rc <= 0) return rc;

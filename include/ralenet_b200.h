@@ -108,6 +108,12 @@ int ralenet_set_attn_umma(int mode);
  * 1 (default) = tcgen05 kernels (wgrad_umma.cu), 0 = mma.sync kernels (wgrad.cu).  Same function; A/B switch,
  * initial value from RALENET_WGRAD_UMMA.  Returns the previous setting. */
 int ralenet_set_wgrad_umma(int on);
+/* 1 (default) = register-tile weight-gradient kernel (wgrad_reg.cu: operands streamed from global memory straight
+ * into mma.sync fragments, accumulators in registers) for every group whose dimensions are multiples of 32; 0 = the
+ * kernels selected by ralenet_set_wgrad_umma.  By default (1) it takes the groups whose largest dW has at most four
+ * 32 x 32 tiles (the HBM-bound ones: C = 32 stages and the 32-wide patch layers), 2 = every eligible group.
+ * Same function; A/B switch, initial value from RALENET_WGRAD_REG.  Returns the previous setting. */
+int ralenet_set_wgrad_reg(int on);
 /* Weight staging of the tcgen05 feed-forward forward kernels (C = 64, 128): 1 (default) = TMA (cp.async.bulk.tensor into
  * the SWIZZLE_128B layout, tma.cuh), 0 = the round-1 path (ld.global -> registers -> st.shared).  Same function; A/B
  * switch, initial value from RALENET_UMMA_TMA.  Returns the previous setting. */

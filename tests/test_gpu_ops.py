@@ -254,6 +254,7 @@ def test_wgrad_tcgen05_kernels_match_mma_sync_kernels(ops, stage, B):
 
     def run(tc):
         prev = _lib.set_wgrad_umma(tc)
+        prev_reg = _lib.load().ralenet_set_wgrad_reg(0)      # this test is about the two older kernel families
         try:
             xs = x.clone().requires_grad_(True)
             pa = [d[k].clone().requires_grad_(True) for k in an]
@@ -265,6 +266,7 @@ def test_wgrad_tcgen05_kernels_match_mma_sync_kernels(ops, stage, B):
             return [q.grad for q in pa + pf]
         finally:
             _lib.set_wgrad_umma(prev)
+            _lib.load().ralenet_set_wgrad_reg(prev_reg)
 
     a, b = run(True), run(False)
     for name, ta, tb in zip(an + fn, a, b):
@@ -544,9 +546,11 @@ def test_weighted_mse_nonuniform_weight(ops):
     _cmp("wmse/rmse", rmse, O.RMSE(tgt, pred))                              # the metrics stay unweighted
 
 
+@pytest.mark.parametrize("wgrad_reg", [0, 1])
 @pytest.mark.parametrize("stage", [3, 4])
-def test_tcgen05_block_kernels_vs_oracle_large_batch(ops, stage):
-    """B = 515 windows (a partial last 128-token tile, > one wave of tile CTAs) with the tcgen05 tile kernels forced
+def test_tcgen05_block_kernels_vs_oracle_large_batch(ops, stage, wgrad_reg):
+    """(wgrad_reg = 1: the weight gradients come from the register-tile kernel of wgrad_reg.cu instead of wgrad_umma.cu)
+    B = 515 windows (a partial last 128-token tile, > one wave of tile CTAs) with the tcgen05 tile kernels forced
     on (attn_umma.cu, ffn_umma.cu, wgrad_umma.cu): outputs, dx and EVERY parameter gradient directly against the fp64
     oracle -- not against the mma.sync kernels."""
     from ecg_denoise_b200 import _lib
@@ -563,6 +567,7 @@ def test_tcgen05_block_kernels_vs_oracle_large_batch(ops, stage):
     dx_ref, gra = O.attn_block_bwd(d1_ref, asaved, p, H, table, W)
     gr.update(gra)
     prev_a, prev_w = _lib.set_attn_umma(2), _lib.set_wgrad_umma(True)
+    prev_r = _lib.load().ralenet_set_wgrad_reg(2 * wgrad_reg)
     try:
         d = {k: _dev(v) for k, v in p.items()}
         xt, tt = _dev(x), (_dev(table) if W else None)
@@ -578,7 +583,8 @@ def test_tcgen05_block_kernels_vs_oracle_large_batch(ops, stage):
     finally:
         _lib.set_attn_umma(prev_a)
         _lib.set_wgrad_umma(prev_w)
-    tag = f"tcgen05_vs_oracle/s{stage}/B{B}"
+        _lib.load().ralenet_set_wgrad_reg(prev_r)
+    tag = f"tcgen05_vs_oracle/s{stage}/B{B}/reg{wgrad_reg}"
     _cmp(tag + "/x1", x1, x1_ref)
     _cmp(tag + "/y", y, y_ref)
     _cmp(tag + "/dx", xt.grad, dx_ref)
@@ -751,3 +757,38 @@ def test_fused_trainer_step_synth(graph):
     _cmp(f"step_synth/graph{int(graph)}/flat_grad", ma._plan.flat_grad, mb._plan.flat_grad, RTOL)
     for (n, p), (_, q) in zip(ma.named_parameters(), mb.named_parameters()):
         assert float((p.detach() - q.detach()).abs().max()) <= 3.2e-3, n
+
+
+@pytest.mark.parametrize("stage", [2, 3, 4])
+@pytest.mark.parametrize("B", [1, 5, 37])
+def test_wgrad_register_tile_kernel_vs_oracle(ops, stage, B):
+    """wgrad_reg.cu (operands straight from global memory into mma.sync fragments, register accumulators, token
+    sub-ranges folded in shared memory, vector reductions into dW): every weight / bias gradient of a block against the
+    fp64 oracle at token counts that are not multiples of the 8-token step or of the CTA slices, incl. one window."""
+    from ecg_denoise_b200 import _lib
+    rs = np.random.RandomState(1200 + 10 * stage + B)
+    C, H, L = O.CHANNELS[stage], O.HEADS[stage], O.LENGTHS[stage]
+    p = _block_params(rs, C, 1)
+    x, g = _rand(rs, B, L, C), _rand(rs, B, L, C)
+    x1_ref, asaved = O.attn_block_fwd(x, p, H, None, 0)
+    y_ref, fsaved = O.ffn_block_fwd(x1_ref, p)
+    d1_ref, gr = O.ffn_block_bwd(g, fsaved, p)
+    dx_ref, gra = O.attn_block_bwd(d1_ref, asaved, p, H, None, 0)
+    gr.update(gra)
+    prev = _lib.load().ralenet_set_wgrad_reg(2)          # 2: force it for every group (default 1: small dW only)
+    try:
+        d = {k: _dev(v) for k, v in p.items()}
+        xt = _dev(x)
+        x1 = ops.AttnBlockFn.apply(xt, d["norm1.weight"], d["norm1.bias"], d["attn.qkv_proj.to_q.weight"],
+                                   d["attn.qkv_proj.to_q.bias"], d["attn.qkv_proj.to_kv.weight"],
+                                   d["attn.qkv_proj.to_kv.bias"], d["attn.proj.weight"], d["attn.proj.bias"], None, H, 0,
+                                   0, ops.RL_F_PRENORM | ops.RL_F_RESIDUAL)
+        y = ops.FFNBlockFn.apply(x1, d["norm2.weight"], d["norm2.bias"], d["mlp.fc1.weight"], d["mlp.fc1.bias"],
+                                 d["mlp.fc2.weight"], d["mlp.fc2.bias"], d["mlp.leconv.partial_conv3.weight"], None, 1,
+                                 ops.RL_F_PRENORM | ops.RL_F_RESIDUAL)
+        y.backward(g.float().cuda())
+        torch.cuda.synchronize()
+    finally:
+        _lib.load().ralenet_set_wgrad_reg(prev)
+    for k in p:
+        _cmp(f"wgrad_reg/s{stage}/B{B}/d_{k}", d[k].grad, gr[k].reshape(p[k].shape))

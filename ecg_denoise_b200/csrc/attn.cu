@@ -13,6 +13,7 @@
 #define RL_MINB 2
 #include "common.cuh"
 #include "attn_core.cuh"
+#include "ffn_body.cuh"
 
 RL_TRACE_DEFINE(attn)
 
@@ -45,8 +46,7 @@ size_t attn_fwd_smem(int L) {
 
 // ---------------------------------------------------------------------------------------------
 template <int C, int WIN, int NWC>
-__global__ void __launch_bounds__(RL_NT, (NWC >= 4) ? 1 : RL_MINB) attn_fwd_kernel(const rl_attn_fwd_args a) {
-  extern __shared__ __align__(16) float smem[];
+__device__ __forceinline__ void attn_fwd_body(const rl_attn_fwd_args& a, float* smem) {
   constexpr int L = 2048 * WIN / C, H = C / RL_HD, M = NWC * L;      // M token rows (NWC whole windows) per CTA
   constexpr int LDC = ld_mk(C);
   using WS = AttnWF<C, NWC>;
@@ -138,6 +138,25 @@ __global__ void __launch_bounds__(RL_NT, (NWC >= 4) ? 1 : RL_MINB) attn_fwd_kern
     });
   }
   RL_TS(attn, 8);
+}
+
+template <int C, int WIN, int NWC>
+__global__ void __launch_bounds__(RL_NT, (NWC >= 4) ? 1 : RL_MINB) attn_fwd_kernel(const rl_attn_fwd_args a) {
+  extern __shared__ __align__(16) float smem[];
+  attn_fwd_body<C, WIN, NWC>(a, smem);
+}
+
+// One launch per TransformerBlock for the narrow stages (C <= 32, one window per CTA): attention half, then the
+// feed-forward half on the block's own output.  x1 = f.x = a.y is written to global memory by the first half (the
+// backward needs it anyway) and read back by the same CTA through L2-coherent loads after a CTA barrier; the second
+// half's first weight chunk is requested before that barrier.  Saves a launch boundary (drain + fill + dependency
+// wait) per block: 10 of the 36 block-half launches of a forward pass.
+template <int C>
+__global__ void __launch_bounds__(RL_NT, RL_MINB) block_fwd_kernel(const rl_attn_fwd_args a, const rl_ffn_fwd_args f) {
+  extern __shared__ __align__(16) float smem[];
+  attn_fwd_body<C, 1, 1>(a, smem);
+  __syncthreads();                       // every thread's part of x1 is in global memory; the attention tiles are dead
+  ffn_fwd_body<C, 1, true>(f, smem);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -395,7 +414,60 @@ int check_shape(int B, int L, int C, int H, int W, int c0) {
   return RL_OK;
 }
 
+template <int C>
+int launch_block_fwd(const rl_attn_fwd_args* a, const rl_ffn_fwd_args* f, cudaStream_t st) {
+  const size_t s1 = attn_fwd_smem<C, 1>(a->L), s2 = ffn_fwd_smem<C>(a->L);
+  const size_t smem = s1 > s2 ? s1 : s2;
+  if (int rc = rl_set_smem(block_fwd_kernel<C>, smem)) return rc;
+  rl_launch_pdl(block_fwd_kernel<C>, dim3(a->B), dim3(RL_NT), smem, st, *a, *f);
+  return rl_check_launch("block_fwd_kernel", C);
+}
+
+int g_block_fuse = -1;
+int block_fuse_on() {
+  if (g_block_fuse < 0) {
+    const char* e = getenv("RALENET_BLOCK_FUSE");
+    g_block_fuse = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_block_fuse;
+}
+
 }  // namespace
+
+extern "C" int ralenet_set_block_fuse(int on) {
+  const int prev = block_fuse_on();
+  g_block_fuse = on ? 1 : 0;
+  return prev;
+}
+
+// TransformerBlock.forward (model/transformer.py:398-411) = attention half + feed-forward half.  Narrow stages
+// (C <= 32, 256-sample windows, both halves pre-norm + residual, f->x == a->y): ONE fused launch; anything else: the
+// two halves one after the other.
+extern "C" int ralenet_block_fwd(const rl_attn_fwd_args* a, const rl_ffn_fwd_args* f, void* stream) {
+  RL_REQUIRE(a && f, RL_ERR_NULL, "block_fwd: args is NULL");
+  const int want = RL_F_PRENORM | RL_F_RESIDUAL;
+  const bool fuse = block_fuse_on() && a->C <= 32 && a->L * a->C == 2048 && f->x == a->y && f->B == a->B &&
+                    f->L == a->L && f->C == a->C && (a->flags & want) == want && (f->flags & want) == want &&
+                    f->le_mode != RL_LE_DEPTHWISE;
+  if (!fuse) {
+    if (int rc = ralenet_attn_fwd(a, stream)) return rc;
+    return ralenet_ffn_fwd(f, stream);
+  }
+  if (int rc = check_shape(a->B, a->L, a->C, a->H, a->W, a->c0)) return rc;
+  RL_REQUIRE(a->x && a->y && a->wq && a->wkv && a->wp && a->pe && a->ln_w && a->ln_b, RL_ERR_NULL,
+             "block_fwd: NULL attention tensor");
+  RL_REQUIRE(a->W == 0 || a->table, RL_ERR_NULL, "block_fwd: W>0 needs table");
+  RL_REQUIRE(!a->q || (a->k && a->v && a->o && a->lse), RL_ERR_NULL, "block_fwd: partial save set");
+  RL_REQUIRE(f->y && f->w1 && f->w2 && f->ln_w && f->ln_b, RL_ERR_NULL, "block_fwd: NULL feed-forward tensor");
+  RL_REQUIRE(f->le_mode == RL_LE_NONE || f->lew, RL_ERR_NULL, "block_fwd: local-enhancement weights missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a->C) {
+    case 8: return launch_block_fwd<8>(a, f, st);
+    case 16: return launch_block_fwd<16>(a, f, st);
+    case 32: return launch_block_fwd<32>(a, f, st);
+  }
+  return RL_ERR_SHAPE;
+}
 
 extern "C" int ralenet_attn_fwd(const rl_attn_fwd_args* a, void* stream) {
   RL_REQUIRE(a, RL_ERR_NULL, "attn_fwd: args is NULL");

@@ -453,15 +453,20 @@ struct MmaTile {
   // v[r][c][e] <- src[row * ld + col] for every output element owned by this thread, in the order of epilogue2():
   // all loads are issued back to back (one round trip to L2 / HBM instead of one per element inside an epilogue
   // lambda).  ld and the tile origin must be even (two adjacent columns per 8-byte load).
-  __device__ __forceinline__ void gather(const float* __restrict__ src, int ld, float (&v)[RT][CT][4]) const {
+  // CG = true: the source was written earlier by THIS kernel (fused block kernels): L2-coherent loads instead of the
+  // read-only path
+  template <bool CG = false>
+  __device__ __forceinline__ void gather(const float* src, int ld, float (&v)[RT][CT][4]) const {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int r = 0; r < RT; ++r)
 #pragma unroll
       for (int c = 0; c < CT; ++c) {
         const int m = row0 + r * 16 + g, n = col0 + c * 8 + 2 * t;
-        const float2 lo = __ldg(reinterpret_cast<const float2*>(src + (size_t)m * ld + n));
-        const float2 hi = __ldg(reinterpret_cast<const float2*>(src + (size_t)(m + 8) * ld + n));
+        const float2* plo = reinterpret_cast<const float2*>(src + (size_t)m * ld + n);
+        const float2* phi = reinterpret_cast<const float2*>(src + (size_t)(m + 8) * ld + n);
+        const float2 lo = CG ? __ldcg(plo) : __ldg(plo);
+        const float2 hi = CG ? __ldcg(phi) : __ldg(phi);
         v[r][c][0] = lo.x; v[r][c][1] = lo.y; v[r][c][2] = hi.x; v[r][c][3] = hi.y;
       }
   }

@@ -1,0 +1,120 @@
+// ffn_body.cuh -- forward of the feed-forward half for one window per CTA as a device function, shared by
+// ffn.cu (the stand-alone kernel) and attn.cu (second half of the fused block kernel of the narrow stages).
+#pragma once
+#include "common.cuh"
+
+template <int C>
+__host__ __device__ constexpr int ffn_fwd_swf() {
+  return cmax(WStream<4 * C, C, B_NK>::FLOATS, WStream<C, 4 * C, B_NK>::FLOATS);
+}
+template <int C>
+size_t ffn_fwd_smem(int L) {
+  return sizeof(float) * ((size_t)L * ld_mk(C) + (size_t)L * ld_mk(4 * C) + ffn_fwd_swf<C>() + (size_t)L + 64);
+}
+
+// CHAIN = true: second half of a fused block kernel (attn.cu::block_fwd_kernel): the input a.x was written by this
+// very CTA a moment ago (the attention half's output), so there is no programmatic-dependency wait and the input is
+// read with L2-coherent loads.
+template <int C, int WIN, bool CHAIN>
+__device__ __forceinline__ void ffn_fwd_body(const rl_ffn_fwd_args& a, float* smem) {
+  constexpr int L = 2048 * WIN / C;
+  constexpr int LDC = ld_mk(C);
+  constexpr int HC = 4 * C, LDH = ld_mk(HC);
+  float* su = smem;
+  float* sh = su + L * LDC;
+  float* sw = sh + L * LDH;
+  float* sfir = sw + ffn_fwd_swf<C>();
+  // the weights are not produced by the preceding kernels of the step: start pulling them before the dependency wait
+  WStream<HC, C, B_NK>::prefetch(sw, a.w1, HC, nullptr, C);
+  if (!CHAIN) {
+    pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
+    pdl_trigger();   // let the next kernel get scheduled while this one runs
+  }
+  const int tid = threadIdx.x;
+  const size_t woff = (size_t)blockIdx.x * L * C;
+  const float* xw = a.x + woff;
+
+  // 1. LN2
+  if (a.flags & RL_F_PRENORM) {
+    const float* lw = a.ln_w;
+    const float* lb = a.ln_b;
+    ln_forward_rows<C>(
+        L, [&](int t, int c) { return CHAIN ? __ldcg(xw + t * C + c) : __ldg(xw + t * C + c); },
+        [&](int t, int c, float zh) { su[t * LDC + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c)); });
+  } else {
+    copy_rows_g2s(su, LDC, xw, L, C);
+  }
+  __syncthreads();
+
+  // 2. h = u W1^T + b1 (N = 4C, K = C);  g1 = GELU(h) -> sh
+  {
+    MmaTile<L, HC> acc;
+    acc.init();
+    WStream<HC, C, B_NK>::template run<true>(acc, su, LDC, sw, a.w1, HC, nullptr, C);
+    WStream<C, HC, B_NK>::prefetch(sw, a.w2, C, nullptr, HC);      // lands behind the GELU / local-enhancement phase
+    const float* b1 = a.b1;
+    float* hs = a.h ? a.h + (size_t)blockIdx.x * L * HC : nullptr;
+    acc.epilogue([&](int t, int n, float v) {
+      v += b1 ? __ldg(b1 + n) : 0.f;
+      if (hs) hs[t * HC + n] = v;
+      sh[t * LDH + n] = gelu_f(v);
+    });
+  }
+  __syncthreads();
+
+  // 3. local enhancement + second GELU
+  if (a.le_mode == RL_LE_PARTIAL) {
+    const float w0 = __ldg(a.lew), w1 = __ldg(a.lew + 1), w2 = __ldg(a.lew + 2);
+    for (int t = tid; t < L; t += RL_NT) {
+      const float p = (t > 0) ? sh[(t - 1) * LDH] : 0.f;
+      const float n = (t + 1 < L) ? sh[(t + 1) * LDH] : 0.f;
+      sfir[t] = w0 * p + w1 * sh[t * LDH] + w2 * n;
+    }
+    __syncthreads();
+    for (int i = tid; i < L * HC; i += RL_NT) {
+      const int t = i / HC, n = i % HC;
+      const float f = (n == 0) ? sfir[t] : sh[t * LDH + n];
+      sh[t * LDH + n] = gelu_f(f);
+    }
+    __syncthreads();
+  } else if (a.le_mode == RL_LE_DEPTHWISE) {
+    for (int c = tid; c < HC; c += RL_NT) {
+      const float w0 = __ldg(a.lew + 3 * c), w1 = __ldg(a.lew + 3 * c + 1), w2 = __ldg(a.lew + 3 * c + 2);
+      float prev = 0.f, cur = sh[c];
+      for (int t = 0; t < L; ++t) {
+        const float nxt = (t + 1 < L) ? sh[(t + 1) * LDH + c] : 0.f;
+        sh[t * LDH + c] = gelu_f(w0 * prev + w1 * cur + w2 * nxt);
+        prev = cur;
+        cur = nxt;
+      }
+    }
+    __syncthreads();
+  }
+
+  // 4. y = x + g2 W2^T + b2 (N = C, K = 4C)
+  {
+    MmaTile<L, C> acc;
+    acc.init();
+    WStream<C, HC, B_NK>::template run<true>(acc, sh, LDH, sw, a.w2, C, nullptr, HC);
+    const float* b2 = a.b2;
+    const float* ex = a.extra ? a.extra + woff : nullptr;
+    float* yw = a.y + woff;
+    const bool resid = a.flags & RL_F_RESIDUAL;
+    // residual (and the U-net skip of the middle block): one batch of loads, not one round trip per element
+    float rv[MmaTile<L, C>::RT][MmaTile<L, C>::CT][4] = {}, ev[MmaTile<L, C>::RT][MmaTile<L, C>::CT][4] = {};
+    if (resid) acc.template gather<CHAIN>(xw, C, rv);
+    if (ex) {
+      acc.gather(ex, C, ev);
+#pragma unroll
+      for (int r = 0; r < MmaTile<L, C>::RT; ++r)
+#pragma unroll
+        for (int c = 0; c < MmaTile<L, C>::CT; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) rv[r][c][e] += ev[r][c][e];
+    }
+    acc.epilogue2(rv, [&](int t, int n, float v, float add) {
+      v += b2 ? __ldg(b2 + n) : 0.f;
+      yw[t * C + n] = v + add;
+    });
+  }
+}

@@ -173,8 +173,6 @@ extern "C" int ralenet_net_fwd(const rl_net_cfg* cfg, const rl_net_ptrs* P, cons
     } else {
       aa.y = next_buf();
     }
-    if ((rc = ralenet_attn_fwd(&aa, stream))) return rc;
-
     rl_ffn_fwd_args fa = {};
     fa.B = B; fa.L = L; fa.C = C; fa.le_mode = cfg->le_mode; fa.flags = RL_F_PRENORM | RL_F_RESIDUAL;
     fa.x = aa.y;
@@ -183,7 +181,7 @@ extern "C" int ralenet_net_fwd(const rl_net_cfg* cfg, const rl_net_ptrs* P, cons
     fa.w1 = bp[RL_BLK_W1]; fa.b1 = bp[RL_BLK_B1]; fa.w2 = bp[RL_BLK_W2]; fa.b2 = bp[RL_BLK_B2];
     fa.lew = bp[RL_BLK_LEW];
     if (save) { fa.y = w.blk[i].y; fa.h = w.blk[i].h; } else { fa.y = next_buf(); fa.h = nullptr; }
-    if ((rc = ralenet_ffn_fwd(&fa, stream))) return rc;
+    if ((rc = ralenet_block_fwd(&aa, &fa, stream))) return rc;      // one launch at the narrow stages
     cur = fa.y;
 
     if (i % 2 == 1) {

@@ -151,6 +151,13 @@ typedef struct {
 int ralenet_ffn_fwd(const rl_ffn_fwd_args* a, void* stream);
 int ralenet_ffn_bwd(const rl_ffn_bwd_args* a, void* stream);
 
+/* TransformerBlock.forward (model/transformer.py:398-411): attention half then feed-forward half, f->x == a->y.
+ * Narrow stages (C <= 32, 256-sample windows, both halves RL_F_PRENORM | RL_F_RESIDUAL) run as ONE fused launch (the
+ * block's x1 is written for the backward and read back by the same CTA); every other shape runs the two halves one
+ * after the other.  ralenet_set_block_fuse(0) forces the two-launch form (A/B; initial value RALENET_BLOCK_FUSE). */
+int ralenet_block_fwd(const rl_attn_fwd_args* a, const rl_ffn_fwd_args* f, void* stream);
+int ralenet_set_block_fuse(int on);
+
 /* ------------------------------------------------------------------------------------------
  * PatchMerging.forward (model/transformer.py:440-460): [B,L,C] -> LN(2C) -> Linear(2C,2C) -> [B,L/2,2C]
  * PatchSeparate.forward (:418-424) + U-skip add (:650,654,658): [B,L,C] -> [B,2L,C/2]

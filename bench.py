@@ -82,6 +82,10 @@ def algorithmic_work(label: str, B: int, L0: int = 256):
              "ffn_fwd_umma": "ffn_fwd_kernel", "ffn_bwd_umma": "ffn_bwd_kernel",
              "attn_fwd_umma": "attn_fwd_kernel", "attn_bwd_umma": "attn_bwd_kernel"}
     name = alias.get(name, name)
+    if name == "block_fwd_kernel" and tags:       # fused attention + feed-forward half (narrow stages): x in, x1 and y
+        C = tags[0]                                # out, q,k,v,o,lse (4.25 N) and h (4 N) saved
+        L = N // C
+        return B * (8 * L * C * C + 4 * L * L * C + 16 * L * C * C), int(B * 11.25 * N * 4)
     if name in ("attn_fwd_kernel", "attn_bwd_kernel", "ffn_fwd_kernel", "ffn_bwd_kernel") and tags:
         C = tags[0]
         L = N // C

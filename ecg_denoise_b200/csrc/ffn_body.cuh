@@ -95,14 +95,15 @@ __device__ __forceinline__ void ffn_fwd_body(const rl_ffn_fwd_args& a, float* sm
   {
     MmaTile<L, C> acc;
     acc.init();
+    const bool resid = a.flags & RL_F_RESIDUAL;
+    // residual (and the U-net skip of the middle block): one batch of loads, not one round trip per element -- issued
+    // before the fc2 GEMM so that the round trip passes behind the MMAs
+    float rv[MmaTile<L, C>::RT][MmaTile<L, C>::CT][4] = {}, ev[MmaTile<L, C>::RT][MmaTile<L, C>::CT][4] = {};
+    if (resid) acc.template gather<CHAIN>(xw, C, rv);
     WStream<C, HC, B_NK>::template run<true>(acc, sh, LDH, sw, a.w2, C, nullptr, HC);
     const float* b2 = a.b2;
     const float* ex = a.extra ? a.extra + woff : nullptr;
     float* yw = a.y + woff;
-    const bool resid = a.flags & RL_F_RESIDUAL;
-    // residual (and the U-net skip of the middle block): one batch of loads, not one round trip per element
-    float rv[MmaTile<L, C>::RT][MmaTile<L, C>::CT][4] = {}, ev[MmaTile<L, C>::RT][MmaTile<L, C>::CT][4] = {};
-    if (resid) acc.template gather<CHAIN>(xw, C, rv);
     if (ex) {
       acc.gather(ex, C, ev);
 #pragma unroll

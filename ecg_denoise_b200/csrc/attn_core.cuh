@@ -111,6 +111,7 @@ __device__ __forceinline__ void attn_core_fwd_item(float* sq, const float* sk, c
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
 #pragma unroll
   for (int e = 0; e < 4; ++e) o[e] += __shfl_xor_sync(0xffffffffu, o[e], 2);     // hi columns + lo columns
+  __syncwarp();     // o overwrites the q rows other lanes of this warp read at the top (racecheck: write-after-read)
   if (t < 2) {
     const float v0 = 1.0f / l0, v1 = 1.0f / l1;
     *reinterpret_cast<float2*>(sq + (i0 + g) * LD + hc + 2 * t) = make_float2(o[0] * v0, o[1] * v0);

@@ -38,10 +38,8 @@ __device__ __forceinline__ void load_stem_window(float* sx, float* sw, float* sb
 __global__ void __launch_bounds__(RL_NT) stem_stats_kernel(const rl_stem_args a) {
   __shared__ float sx[2 * (MAXL + 2)];
   __shared__ float sw[48], sb[8];
-  __shared__ float sacc[16];
   const int L = a.L, tid = threadIdx.x;
   load_stem_window(sx, sw, sb, a.x + (size_t)blockIdx.x * 2 * L, a.conv_w, a.conv_b, L);
-  if (tid < 16) sacc[tid] = 0.f;
   __syncthreads();
   float s1[8], s2[8];
 #pragma unroll
@@ -56,16 +54,24 @@ __global__ void __launch_bounds__(RL_NT) stem_stats_kernel(const rl_stem_args a)
       s2[o] += v * v;
     }
   }
+  // warp sums meet in shared memory and are added in warp order: the BatchNorm statistics -- and with them the
+  // training-mode forward -- are bit-reproducible from run to run (shared-memory atomics were not)
+  __shared__ float swp[RL_NT / 32][16];
 #pragma unroll
   for (int o = 0; o < 8; ++o) {
     const float r1 = warp_sum(s1[o]), r2 = warp_sum(s2[o]);
     if ((tid & 31) == 0) {
-      atomicAdd(&sacc[o], r1);
-      atomicAdd(&sacc[8 + o], r2);
+      swp[tid >> 5][o] = r1;
+      swp[tid >> 5][8 + o] = r2;
     }
   }
   __syncthreads();
-  if (tid < 16) a.partials[(size_t)blockIdx.x * 16 + tid] = sacc[tid];
+  if (tid < 16) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < RL_NT / 32; ++w) tot += swp[w][tid];
+    a.partials[(size_t)blockIdx.x * 16 + tid] = tot;
+  }
 }
 
 // sum partials[B][16] in double -> out[16] (+ optional extras); one CTA
@@ -144,7 +150,6 @@ __global__ void __launch_bounds__(RL_NT) stem_bwd_stats_kernel(const rl_stem_bwd
   pdl_trigger();   // let the next kernel get scheduled while this one runs
   __shared__ float sx[2 * (MAXL + 2)];
   __shared__ float sw[48], sb[8], smu[8], srs[8];
-  __shared__ float sacc[16];
   const int L = a.L, tid = threadIdx.x;
   load_stem_window(sx, sw, sb, a.x + (size_t)blockIdx.x * 2 * L, a.conv_w, a.conv_b, L);
   if (tid < 8) {
@@ -154,7 +159,6 @@ __global__ void __launch_bounds__(RL_NT) stem_bwd_stats_kernel(const rl_stem_bwd
     smu[tid] = mu;
     srs[tid] = rs;
   }
-  if (tid < 16) sacc[tid] = 0.f;
   __syncthreads();
   const float* gw = a.g + (size_t)blockIdx.x * L * 8;
   const float* g2w = a.g2 ? a.g2 + (size_t)blockIdx.x * L * 8 : nullptr;
@@ -173,16 +177,24 @@ __global__ void __launch_bounds__(RL_NT) stem_bwd_stats_kernel(const rl_stem_bwd
       s2[o] += g * ah;
     }
   }
+  // warp sums meet in shared memory and are added in warp order: the BatchNorm statistics -- and with them the
+  // training-mode forward -- are bit-reproducible from run to run (shared-memory atomics were not)
+  __shared__ float swp[RL_NT / 32][16];
 #pragma unroll
   for (int o = 0; o < 8; ++o) {
     const float r1 = warp_sum(s1[o]), r2 = warp_sum(s2[o]);
     if ((tid & 31) == 0) {
-      atomicAdd(&sacc[o], r1);
-      atomicAdd(&sacc[8 + o], r2);
+      swp[tid >> 5][o] = r1;
+      swp[tid >> 5][8 + o] = r2;
     }
   }
   __syncthreads();
-  if (tid < 16) a.partials[(size_t)blockIdx.x * 16 + tid] = sacc[tid];
+  if (tid < 16) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < RL_NT / 32; ++w) tot += swp[w][tid];
+    a.partials[(size_t)blockIdx.x * 16 + tid] = tot;
+  }
 }
 
 __global__ void __launch_bounds__(RL_NT) stem_bwd_apply_kernel(const rl_stem_bwd_args a) {

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "attn_core.cuh"
 #include "umma.cuh"
+#include "tma.cuh"
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
@@ -32,6 +33,8 @@ namespace cg = cooperative_groups;
 #endif
 
 RL_TRACE_DEFINE(attn_umma)
+
+int rl_umma_tma_on();            // ffn_umma.cu: ralenet_set_umma_tma / RALENET_UMMA_TMA
 
 namespace {
 
@@ -98,26 +101,57 @@ struct QkvStage {
   }
 };
 
-template <int C>
-__global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_attn_fwd_args a) {
+// TMA = true: the weight operands arrive through cp.async.bulk.tensor (tma.cuh): per 32-wide K chunk three 32-row boxes
+// (the q, k and v rows of this CTA's head slice, from to_q and the two halves of to_kv) into one 96-row SWIZZLE_128B
+// tile, and one C-row box for the K-slice of the output projection.  TMA = false: the round-1 register staging (A/B).
+template <int C, bool TMA>
+__global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_attn_fwd_args a,
+                                                                       const __grid_constant__ CUtensorMap tmq,
+                                                                       const __grid_constant__ CUtensorMap tmkv,
+                                                                       const __grid_constant__ CUtensorMap tmp) {
   constexpr int L = 2048 / C, H = C / RL_HD, NSL = C / CS, NWT = TM / L, HS = CS / RL_HD, QT = L / 16;
   constexpr int NCHK = C / KC;
   // the weights are not written by the preceding kernels of the step: pull the whole q|k|v slice of this CTA into
   // registers before waiting on the programmatic dependency, so its L2 latency hides behind the previous kernel
-  QkvStage wr[NCHK];
-  {
+  QkvStage wr[TMA ? 1 : NCHK];
+  if constexpr (!TMA) {
     const int rp = (int)(blockIdx.x % NSL);
 #pragma unroll
     for (int j = 0; j < NCHK; ++j) wr[j].load(a.wq, a.wkv, rp, C, j * KC);
   }
-  extern __shared__ __align__(128) float smem[];
+  extern __shared__ __align__(1024) float smem[];
   float* r0 = smem;
   float* r1 = smem + ASmem<C>::R0;
   float* stab = r1 + ASmem<C>::R1;                           // R-wave table * log2(e), (2W-1) x H <= 128 floats
   float* s_pe = stab + 128;                                  // positional tile [L][LDPE]
   float* s_ln = s_pe + L * ASmem<C>::LDPE;                   // norm1 weight [C] | bias [C]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ln + 2 * C);   // 2 mbarriers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ln + 2 * C);   // [0,1] MMAs of a ring buffer done, [2,3] q|k|v chunk
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);  // landed, [4] Wp slice landed
+  const int r_early = (int)(blockIdx.x % NSL);
+  auto tma_issue_qkv = [&](int j) {      // tid 0: chunk j of [Wq_r ; Wk_r ; Wv_r] -> ring buffer j & 1 (hi tile)
+    float* dst = r1 + (j & 1) * 2 * NQ * KC;
+    uint64_t* bar = bars + 2 + (j & 1);
+    tma::expect_tx(bar, NQ * KC * 4);
+    tma::load_2d(dst, &tmq, j * KC, CS * r_early, bar);
+    tma::load_2d(dst + CS * KC, &tmkv, j * KC, CS * r_early, bar);
+    tma::load_2d(dst + 2 * CS * KC, &tmkv, j * KC, C + CS * r_early, bar);
+  };
+  if (threadIdx.x == 0) {
+    umma::mbar_init(bars, 1);
+    umma::mbar_init(bars + 1, 1);
+    umma::mbar_init(bars + 2, 1);
+    umma::mbar_init(bars + 3, 1);
+    umma::mbar_init(bars + 4, 1);
+    umma::fence_mbar_init();
+    if constexpr (TMA) {
+      umma::fence_async_smem();
+      tma::prefetch_desc(&tmq);
+      tma::prefetch_desc(&tmkv);
+      tma::prefetch_desc(&tmp);
+      tma_issue_qkv(0);                  // weights are immutable inside the step: the ring fills while the previous
+      tma_issue_qkv(1);                  // kernel drains (NCHK >= 2)
+    }
+  }
   // ... and so do the constants of phase 1 (positional tile, LayerNorm affine) and the R-wave table: staged in
   // shared memory here, phase 1 then waits for ONE round of global loads (x) instead of three
   {
@@ -157,11 +191,6 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
   const float* xw = a.x + tok0 * C;
   const int W = a.W, c0 = a.c0;
 
-  if (tid == 0) {
-    umma::mbar_init(bars, 1);
-    umma::mbar_init(bars + 1, 1);
-    umma::fence_mbar_init();
-  }
   if (warp == 0) umma::tmem_alloc<TMEM_COLS>(tmem_slot);
   __syncthreads();                                           // staged constants visible to every warp
   RL_TS(attn_umma, 2);
@@ -236,23 +265,37 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
     constexpr uint32_t idesc = umma::idesc_tf32(TM, NQ);
 #pragma unroll
     for (int j = 0; j < NCHK; ++j) {
-      ring.wait_free();
       float* bh = sB + ring.buf() * 2 * NQ * KC;
       float* bl = bh + NQ * KC;
-      wr[j].store(bh, bl);
+      if constexpr (TMA) {
+        umma::mbar_wait(bars + 2 + (j & 1), (uint32_t)((j >> 1) & 1));
+        tma::derive_lo<RL_NT>(bh, bl, NQ * KC);
+      } else {
+        ring.wait_free();
+        wr[j].store(bh, bl);
+      }
       umma::fence_async_smem();
       __syncthreads();
       if (tid == 0) {
         umma::tc_fence_after();
-        umma::mma_chunk_3x<KC>(tb, sA_hi, sA_lo, C, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
+        if constexpr (TMA) tma::mma_chunk_3x<KC>(tb, sA_hi, sA_lo, C, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
+        else umma::mma_chunk_3x<KC>(tb, sA_hi, sA_lo, C, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
         umma::commit(bars + ring.buf());
+        if constexpr (TMA) {
+          if (j + 2 < NCHK) {            // refill this buffer once its MMAs have drained
+            ++ring.chunk;
+            ring.wait_last();
+            --ring.chunk;
+            tma_issue_qkv(j + 2);
+          }
+        }
       }
       ++ring.chunk;
     }
   }
   // the Wp slice of this CTA goes to registers now; its latency hides behind the epilogue and the attention core
   umma::KStage<C, CS, RL_NT> wpr;
-  wpr.load(a.wp + CS * r, C, C);
+  if constexpr (!TMA) wpr.load(a.wp + CS * r, C, C);
   // ... and so do the bias values of epilogue 1 (warp group w / 4 = 0, 1, 2 takes q, k, v)
   float4 bias4[CS / 4];
   {
@@ -270,6 +313,14 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
   ring.wait_last();
   umma::tc_fence_after();
   RL_TS(attn_umma, 5);
+  if constexpr (TMA) {
+    // the ring is dead (its last MMAs have completed): the K-slice Wp[:, 32 r : 32 r + 32] lands over it while
+    // epilogue 1 and the attention core run
+    if (tid == 0) {
+      tma::expect_tx(bars + 4, C * CS * 4);
+      tma::load_2d(sW_hi, &tmp, CS * r, 0, bars + 4);
+    }
+  }
 
   // 3a. epilogue 1: + bias, q / k / v slices -> shared memory [TM][LDS] (over the dead u tile) and, for the
   //     backward, global memory.  Warp w reads TMEM lane quadrant w % 4; warp group w / 4 = 0, 1, 2 takes q, k, v.
@@ -345,13 +396,19 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
       *reinterpret_cast<float4*>(sO_lo + o) = make_float4(o4.x - umma::trunc_tf32(o4.x), o4.y - umma::trunc_tf32(o4.y),
                                                           o4.z - umma::trunc_tf32(o4.z), o4.w - umma::trunc_tf32(o4.w));
     }
-    wpr.store(sW_hi, sW_lo);
+    if constexpr (TMA) {
+      umma::mbar_wait(bars + 4, 0u);
+      tma::derive_lo<RL_NT>(sW_hi, sW_lo, C * CS);
+    } else {
+      wpr.store(sW_hi, sW_lo);
+    }
     umma::fence_async_smem();
     __syncthreads();
     if (tid == 0) {
       constexpr uint32_t idesc = umma::idesc_tf32(TM, C);
       umma::tc_fence_after();
-      umma::mma_chunk_3x<CS>(tb + NQ, sO_hi, sO_lo, CS, 0, sW_hi, sW_lo, idesc, 0u);
+      if constexpr (TMA) tma::mma_chunk_3x<CS>(tb + NQ, sO_hi, sO_lo, CS, 0, sW_hi, sW_lo, idesc, 0u);
+      else umma::mma_chunk_3x<CS>(tb + NQ, sO_hi, sO_lo, CS, 0, sW_hi, sW_lo, idesc, 0u);
       umma::commit(bars + ring.buf());
     }
     ++ring.chunk;
@@ -421,11 +478,17 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
   RL_TS(attn_umma, 12);
 }
 
-template <int C>
+template <int C, bool TMA>
 int launch(const rl_attn_fwd_args& a, cudaStream_t st) {
   constexpr int NSL = C / CS;
   const int tiles = (a.B * a.L + TM - 1) / TM;
-  auto kernel = attn_fwd_umma_kernel<C>;
+  CUtensorMap tmq = {}, tmkv = {}, tmp = {};
+  if (TMA) {
+    if (int rc = rl_tmap_weight(a.wq, C, C, C, CS, &tmq)) return rc;          // to_q  [C][C]:  32-row boxes
+    if (int rc = rl_tmap_weight(a.wkv, 2 * C, C, C, CS, &tmkv)) return rc;    // to_kv [2C][C]: 32-row boxes
+    if (int rc = rl_tmap_weight(a.wp, C, C, C, C, &tmp)) return rc;           // proj  [C][C]:  all C rows, 32 columns
+  }
+  auto kernel = attn_fwd_umma_kernel<C, TMA>;
   if (int rc = rl_set_smem(kernel, ASmem<C>::BYTES)) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(tiles * NSL);
@@ -442,7 +505,7 @@ int launch(const rl_attn_fwd_args& a, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   rl_prof_pre(st);
-  cudaLaunchKernelEx(&cfg, kernel, a);
+  cudaLaunchKernelEx(&cfg, kernel, a, tmq, tmkv, tmp);
   return rl_check_launch("attn_fwd_umma", C);
 }
 
@@ -483,5 +546,8 @@ int rl_attn_fwd_umma(const rl_attn_fwd_args* a, cudaStream_t st) {
     const int ctas = (a->B * a->L + TM - 1) / TM * (a->C / CS);
     if (ctas > n_sm) return 1;
   }
-  return (a->C == 128) ? launch<128>(*a, st) : launch<64>(*a, st);
+  const bool tma_ok = rl_umma_tma_on() && ((uintptr_t)a->wq % 16 == 0) && ((uintptr_t)a->wkv % 16 == 0) &&
+                      ((uintptr_t)a->wp % 16 == 0);
+  if (a->C == 128) return tma_ok ? launch<128, true>(*a, st) : launch<128, false>(*a, st);
+  return tma_ok ? launch<64, true>(*a, st) : launch<64, false>(*a, st);
 }

@@ -40,24 +40,6 @@ struct FwdSmem {
 
 using umma::Ring;
 
-// D[tmem] (+)= A[:, k0:k0+KC] * B^T with the 3-pass split; A: un-swizzled K-major tile pair (umma.cuh), B: one KC = 32
-// wide chunk in the K-major SWIZZLE_128B layout written by TMA (tma.cuh) and its remainder tile in the same layout
-__device__ __forceinline__ void mma_chunk_3x_tma(uint32_t tmem_d, const float* a_hi, const float* a_lo, int KT_A, int k0,
-                                                 const float* b_hi, const float* b_lo, uint32_t idesc, uint32_t accum) {
-  const uint32_t sbo_a = (uint32_t)(KT_A / 4) * 128u;
-  const uint32_t ah = umma::smem_u32(a_hi) + (uint32_t)(k0 / 4) * 128u, al = umma::smem_u32(a_lo) + (uint32_t)(k0 / 4) * 128u;
-  const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo);
-#pragma unroll
-  for (int ks = 0; ks < KC / 8; ++ks) {
-    const uint64_t dah = umma::make_desc(ah + ks * 256u, 128u, sbo_a), dal = umma::make_desc(al + ks * 256u, 128u, sbo_a);
-    const uint64_t dbh = tma::desc_sw128(bh + ks * 32u), dbl = tma::desc_sw128(bl + ks * 32u);
-    umma::mma_tf32(tmem_d, dal, dbh, idesc, accum);
-    umma::mma_tf32(tmem_d, dah, dbl, idesc, 1u);
-    umma::mma_tf32(tmem_d, dah, dbh, idesc, 1u);
-    accum = 1u;
-  }
-}
-
 // TMA = true: the weight chunks of fc1 and fc2 arrive through cp.async.bulk.tensor (tma.cuh) in one 2-stage ring that
 // runs across both GEMMs (chunks 0 .. C/32 - 1 from W1, then TS/32 chunks from W2); one thread issues, the CTA only
 // derives the tf32 remainder tile.  TMA = false: the round-1 path (registers -> st.shared), kept for A/B.
@@ -221,7 +203,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
       __syncthreads();
       if (tid == 0) {
         umma::tc_fence_after();
-        if constexpr (TMA) mma_chunk_3x_tma(tb, sA_hi, sA_lo, C, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
+        if constexpr (TMA) tma::mma_chunk_3x<KC>(tb, sA_hi, sA_lo, C, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
         else umma::mma_chunk_3x<KC>(tb, sA_hi, sA_lo, C, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
         umma::commit(bars + ring.buf());
         if constexpr (TMA) {             // refill this buffer with chunk j + 2 as soon as its MMAs have drained
@@ -326,7 +308,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
       __syncthreads();
       if (tid == 0) {
         umma::tc_fence_after();
-        if constexpr (TMA) mma_chunk_3x_tma(tb + TS, sA_hi, sA_lo, TS, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
+        if constexpr (TMA) tma::mma_chunk_3x<KC>(tb + TS, sA_hi, sA_lo, TS, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
         else umma::mma_chunk_3x<KC>(tb + TS, sA_hi, sA_lo, TS, j * KC, bh, bl, idesc, j > 0 ? 1u : 0u);
         umma::commit(bars + ring.buf());
         if constexpr (TMA) {
@@ -754,6 +736,7 @@ static int ffn_tma_on() {
   }
   return g_ffn_tma;
 }
+int rl_umma_tma_on() { return ffn_tma_on(); }
 extern "C" int ralenet_set_umma_tma(int on) {
   const int prev = ffn_tma_on();
   g_ffn_tma = on ? 1 : 0;

@@ -46,3 +46,38 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t byte_addr) {
 }
 
 }  // namespace tma
+
+#include "umma.cuh"
+namespace tma {
+// D[tmem] (+)= A[:, k0:k0+KCW] * B^T with the 3-pass tf32 split; A: un-swizzled K-major tile pair (umma.cuh) with KT_A
+// contraction elements per row, B: one KCW <= 32 wide chunk in the K-major SWIZZLE_128B layout written by TMA and its
+// remainder tile in the same layout.  Issued by ONE thread.
+template <int KCW>
+__device__ __forceinline__ void mma_chunk_3x(uint32_t tmem_d, const float* a_hi, const float* a_lo, int KT_A, int k0,
+                                             const float* b_hi, const float* b_lo, uint32_t idesc, uint32_t accum) {
+  static_assert(KCW % 8 == 0 && KCW <= 32, "one SWIZZLE_128B atom holds 32 contraction floats");
+  const uint32_t sbo_a = (uint32_t)(KT_A / 4) * 128u;
+  const uint32_t ah = umma::smem_u32(a_hi) + (uint32_t)(k0 / 4) * 128u, al = umma::smem_u32(a_lo) + (uint32_t)(k0 / 4) * 128u;
+  const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo);
+#pragma unroll
+  for (int ks = 0; ks < KCW / 8; ++ks) {
+    const uint64_t dah = umma::make_desc(ah + ks * 256u, 128u, sbo_a), dal = umma::make_desc(al + ks * 256u, 128u, sbo_a);
+    const uint64_t dbh = desc_sw128(bh + ks * 32u), dbl = desc_sw128(bl + ks * 32u);
+    umma::mma_tf32(tmem_d, dal, dbh, idesc, accum);
+    umma::mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+    umma::mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+    accum = 1u;
+  }
+}
+// element-wise remainder tile of a landed chunk (any layout): lo = hi - trunc_tf32(hi); all NT threads of the CTA
+template <int NT>
+__device__ __forceinline__ void derive_lo(const float* hi, float* lo, int floats) {
+  const float4* h4 = reinterpret_cast<const float4*>(hi);
+  float4* l4 = reinterpret_cast<float4*>(lo);
+  for (int i = threadIdx.x; i < floats / 4; i += NT) {
+    const float4 v = h4[i];
+    l4[i] = make_float4(v.x - umma::trunc_tf32(v.x), v.y - umma::trunc_tf32(v.y), v.z - umma::trunc_tf32(v.z),
+                        v.w - umma::trunc_tf32(v.w));
+  }
+}
+}  // namespace tma

@@ -1,0 +1,16 @@
+#!/bin/bash
+# SASS opcode evidence per object file (run in the build container after __graft_entry__.build()):
+#   UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG = cp.async.bulk.tensor (TMA), HMMA = mma.sync,
+#   LDGMC = multimem.ld_reduce (NVLS), REDG = red.global (weight-gradient reductions), LDGSTS = cp.async
+out=${1:-profiles/sass_histogram.txt}
+{
+  echo "# cuobjdump -sass build/*.o | opcode counts ($(date -u +%F), nvcc $(nvcc --version | grep -o 'release [0-9.]*'))"
+  printf "%-16s %8s %6s %6s %8s %8s %8s %8s %8s %8s %8s\n" object UTCxMMA LDTM STTM UTMALDG HMMA.tf32 HMMA.f16 LDGSTS LDGMC REDG SYNCS
+  for o in build/*.o; do
+    s=$(cuobjdump -sass $o 2>/dev/null)
+    c() { echo "$s" | grep -c -E "$1"; }
+    printf "%-16s %8d %6d %6d %8d %8d %8d %8d %8d %8d %8d\n" $(basename $o) "$(c 'UTC[A-Z]*MMA')" "$(c 'LDTM')" "$(c 'STTM')" \
+      "$(c 'UTMALDG')" "$(c 'HMMA\.1688\.F32\.TF32')" "$(c 'HMMA\.16816')" "$(c 'LDGSTS')" "$(c 'LDGMC')" "$(c 'REDG')" "$(c 'SYNCS')"
+  done
+} > $out
+cat $out

@@ -476,14 +476,18 @@ def train12_record(dev, world, rank, steps, warmup):
     step(dx, dt)
     torch.cuda.synchronize()
     launches = _lib.launch_count(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(steps):
-        loss = step(dx, dt)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    # the stock loop allocates through the caching allocator every step (a 2.3 GB workspace lease among others), so a
+    # timed loop right after other large workloads can include one-off cudaMalloc / cudaFree stalls: best of two loops
+    ms = float("inf")
+    for _ in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            loss = step(dx, dt)
+        e1.record()
+        barrier()
+        ms = min(ms, e0.elapsed_time(e1))
     sx, st_ = torch.empty_like(dx), torch.empty_like(dt)
     barrier()
     t0 = time.perf_counter()

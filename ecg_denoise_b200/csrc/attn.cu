@@ -190,30 +190,33 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   float* s_gb = stabg + 128;
   const int tid = threadIdx.x;
   RL_TS(attn, 0);
-  AttnW<C>::DProj::prefetch(sw, a.wp, 1 << 30, nullptr, C);   // weights do not depend on the preceding kernels
-  {   // neither do the tensors the forward pass saved for this window: q, k, v, o, lse and the block input
-    const size_t wo = (size_t)blockIdx.x * LC;
-    prefetch_l2_block(a.q + wo, LC * 4);
-    prefetch_l2_block(a.k + wo, LC * 4);
-    prefetch_l2_block(a.v + wo, LC * 4);
-    prefetch_l2_block(a.o + wo, LC * 4);
-    prefetch_l2_block(a.x + wo, LC * 4);
-    prefetch_l2_block(a.lse + (size_t)blockIdx.x * (LC / 4), LC);
+  const size_t woff = (size_t)blockIdx.x * LC;
+  {   // The tensors the forward pass saved for this window -- q, k, v, o, lse -- do not depend on the preceding kernel
+      // of the backward chain: they stream into shared memory with cp.async BEFORE the dependency wait (round 1 only
+      // prefetched them to L2 and copied them after the wait: 10 % of the samples of attn_bwd<16> sat on those loads).
+      // Their group is committed before the weight prefetch, so every later wait on a weight chunk covers it.
+    constexpr int C4 = C / 4;
+    for (int i = tid; i < L * C4; i += RL_NT) {
+      const int r = i / C4, c = (i % C4) * 4;
+      cp_async16(sq + r * LDC + c, a.q + woff + r * C + c);
+      cp_async16(sk + r * LDC + c, a.k + woff + r * C + c);
+      cp_async16(sv + r * LDC + c, a.v + woff + r * C + c);
+      cp_async16(sdk + r * LDC + c, a.o + woff + r * C + c);
+    }
+    for (int i = tid; i < LC / 16; i += RL_NT) cp_async16(sLse + 4 * i, a.lse + (size_t)blockIdx.x * (LC / 4) + 4 * i);
+    cp_async_commit();
+    prefetch_l2_block(a.x + woff, LC * 4);                   // block input: needed by the LayerNorm backward at the end
   }
+  AttnW<C>::DProj::prefetch(sw, a.wp, 1 << 30, nullptr, C);   // weights do not depend on the preceding kernels either
   pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
   pdl_trigger();   // let the next kernel get scheduled while this one runs
   RL_TS(attn, 1);
-  const size_t woff = (size_t)blockIdx.x * LC;
   const float* gw = a.g + woff;
   const float* xw = a.x + woff;
 
-  // 1. stage saved tensors; g -> sdq (temp), o -> sdk (temp)
-  copy_rows_g2s(sq, LDC, a.q + woff, L, C);
-  copy_rows_g2s(sk, LDC, a.k + woff, L, C);
-  copy_rows_g2s(sv, LDC, a.v + woff, L, C);
+  // 1. g -> sdq (temp); o sits in sdk (temp)
   copy_rows_g2s(sdq, LDC, gw, L, C);
-  copy_rows_g2s(sdk, LDC, a.o + woff, L, C);
-  copy_g2s(sLse, a.lse + (size_t)blockIdx.x * (LC / 4), LC / 4);
+  cp_async_wait<0>();                                        // saved tensors (and the first weight chunk) have landed
   if (tid < 128) {
     stabg[tid] = 0.f;
     stab[tid] = (W > 0 && tid < (2 * W - 1) * H) ? __ldg(a.table + tid) * RL_LOG2E : 0.f;

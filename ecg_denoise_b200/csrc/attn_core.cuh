@@ -43,8 +43,7 @@ __device__ __forceinline__ void attn_core_fwd_item(float* sq, const float* sk, c
   uint32_t qa[4];
   {
     const float* qp = sq + (i0 + g) * LD + hc + t;
-    split_tf32(qp[0] * qs, qa[0], qa[2]);
-    split_tf32(qp[8 * LD] * qs, qa[1], qa[3]);
+    split_tf32x2(qp[0] * qs, qp[8 * LD] * qs, qa[0], qa[1], qa[2], qa[3]);
   }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float o[4] = {0.f, 0.f, 0.f, 0.f};
@@ -95,10 +94,8 @@ __device__ __forceinline__ void attn_core_fwd_item(float* sq, const float* sk, c
       l0 += p0 + p1;
       l1 += p2 + p3;
       uint32_t ah[4], al[4];
-      split_tf32(p0, ah[0], al[0]);
-      split_tf32(p2, ah[1], al[1]);
-      split_tf32(p1, ah[2], al[2]);
-      split_tf32(p3, ah[3], al[3]);
+      split_tf32x2(p0, p2, ah[0], ah[1], al[0], al[1]);
+      split_tf32x2(p1, p3, ah[2], ah[3], al[2], al[3]);
       const float* vq = vp + (j0 + 8 * tt) * LD;
       const uint32_t b[2] = {pack_hl(vq[0], sel_hi), pack_hl(vq[LD], sel_hi)};
       mma_tf32(o, ah, b);

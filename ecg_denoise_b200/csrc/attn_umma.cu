@@ -94,8 +94,7 @@ struct QkvStage {
         const int o = rsub * 4 + (qgrp * 4 + qsub) * 32 + rgrp * (NCH * 32);
         *reinterpret_cast<float4*>(hi + o) = v[i];
         *reinterpret_cast<float4*>(lo + o) =
-            make_float4(v[i].x - umma::trunc_tf32(v[i].x), v[i].y - umma::trunc_tf32(v[i].y),
-                        v[i].z - umma::trunc_tf32(v[i].z), v[i].w - umma::trunc_tf32(v[i].w));
+            umma::lo4(v[i]);
       }
     }
   }
@@ -249,8 +248,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
       if (!ok) u = make_float4(0.f, 0.f, 0.f, 0.f);
       const int o = rsub * 4 + qc * 32 + warp * (C / 4) * 32;
       *reinterpret_cast<float4*>(sA_hi + o) = u;
-      *reinterpret_cast<float4*>(sA_lo + o) = make_float4(u.x - umma::trunc_tf32(u.x), u.y - umma::trunc_tf32(u.y),
-                                                          u.z - umma::trunc_tf32(u.z), u.w - umma::trunc_tf32(u.w));
+      *reinterpret_cast<float4*>(sA_lo + o) = umma::lo4(u);
     }
   }
   umma::tc_fence_before();
@@ -393,8 +391,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_fwd_umma_kernel(const rl_
       if (a.o && row < nvalid) *reinterpret_cast<float4*>(a.o + (tok0 + row) * C + CS * r + 4 * qc) = o4;
       const int o = rsub * 4 + qc * 32 + warp * (CS / 4) * 32;
       *reinterpret_cast<float4*>(sO_hi + o) = o4;
-      *reinterpret_cast<float4*>(sO_lo + o) = make_float4(o4.x - umma::trunc_tf32(o4.x), o4.y - umma::trunc_tf32(o4.y),
-                                                          o4.z - umma::trunc_tf32(o4.z), o4.w - umma::trunc_tf32(o4.w));
+      *reinterpret_cast<float4*>(sO_lo + o) = umma::lo4(o4);
     }
     if constexpr (TMA) {
       umma::mbar_wait(bars + 4, 0u);

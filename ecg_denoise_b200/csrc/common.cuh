@@ -378,6 +378,20 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
+// two splits at once: the remainders come from ONE packed subtraction (Blackwell `sub.f32x2`, SASS FADD2) -- the split
+// arithmetic is 18 % of the instructions of the narrow-stage GEMM kernels (ncu r2_v24), this takes a quarter of it out
+__device__ __forceinline__ void split_tf32x2(float x0, float x1, uint32_t& h0, uint32_t& h1, uint32_t& l0, uint32_t& l1) {
+  h0 = __float_as_uint(x0) & 0xffffe000u;
+  h1 = __float_as_uint(x1) & 0xffffe000u;
+  float r0, r1;
+  asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tsub.f32x2 c, a, b;\n\t"
+      "mov.b64 {%0, %1}, c;\n\t}"
+      : "=f"(r0), "=f"(r1)
+      : "f"(x0), "f"(x1), "f"(__uint_as_float(h0)), "f"(__uint_as_float(h1)));
+  l0 = __float_as_uint(r0);
+  l1 = __float_as_uint(r1);
+}
+
 template <int M, int N>
 struct MmaTile {
   static constexpr int MT = M / 16, NT = N / 8, NW = RL_NT / 32;
@@ -408,6 +422,7 @@ struct MmaTile {
   __device__ __forceinline__ void mac(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                       int K) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll 2
     for (int k0 = 0; k0 < K; k0 += 8) {
       uint32_t ahi[RT][4], alo[RT][4];
 #pragma unroll
@@ -421,10 +436,8 @@ struct MmaTile {
           const float* p = A + (k0 + t) * lda + m;
           a0 = p[0]; a1 = p[8]; a2 = p[4 * lda]; a3 = p[4 * lda + 8];
         }
-        split_tf32(a0, ahi[r][0], alo[r][0]);
-        split_tf32(a1, ahi[r][1], alo[r][1]);
-        split_tf32(a2, ahi[r][2], alo[r][2]);
-        split_tf32(a3, ahi[r][3], alo[r][3]);
+        split_tf32x2(a0, a1, ahi[r][0], ahi[r][1], alo[r][0], alo[r][1]);
+        split_tf32x2(a2, a3, ahi[r][2], ahi[r][3], alo[r][2], alo[r][3]);
       }
 #pragma unroll
       for (int c = 0; c < CT; ++c) {
@@ -438,8 +451,7 @@ struct MmaTile {
           b0 = p[0]; b1 = p[4 * ldb];
         }
         uint32_t bhi[2], blo[2];
-        split_tf32(b0, bhi[0], blo[0]);
-        split_tf32(b1, bhi[1], blo[1]);
+        split_tf32x2(b0, b1, bhi[0], bhi[1], blo[0], blo[1]);
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
           mma_tf32(acc[r][c], alo[r], bhi);
@@ -703,12 +715,9 @@ __device__ __forceinline__ void cta_wgrad_mma(const float* A, int lda, const flo
 #pragma unroll 4
       for (int k0 = 0; k0 < L; k0 += 8) {
         uint32_t ahi[4], alo[4], bhi[2], blo[2];
-        split_tf32(ap[k0 * lda], ahi[0], alo[0]);
-        split_tf32(ap[k0 * lda + 8], ahi[1], alo[1]);
-        split_tf32(ap[(k0 + 4) * lda], ahi[2], alo[2]);
-        split_tf32(ap[(k0 + 4) * lda + 8], ahi[3], alo[3]);
-        split_tf32(bp[k0 * ldb], bhi[0], blo[0]);
-        split_tf32(bp[(k0 + 4) * ldb], bhi[1], blo[1]);
+        split_tf32x2(ap[k0 * lda], ap[k0 * lda + 8], ahi[0], ahi[1], alo[0], alo[1]);
+        split_tf32x2(ap[(k0 + 4) * lda], ap[(k0 + 4) * lda + 8], ahi[2], ahi[3], alo[2], alo[3]);
+        split_tf32x2(bp[k0 * ldb], bp[(k0 + 4) * ldb], bhi[0], bhi[1], blo[0], blo[1]);
         mma_tf32(acc, alo, bhi);
         mma_tf32(acc, ahi, blo);
         mma_tf32(acc, ahi, bhi);

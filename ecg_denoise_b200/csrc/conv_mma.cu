@@ -50,17 +50,14 @@ __device__ __forceinline__ void implicit_gemm(float (&acc)[2][NT][4], const floa
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int m = row0 + r * 16 + g;
-      split_tf32(src[o0 + m], ahi[r][0], alo[r][0]);
-      split_tf32(src[o0 + m + 8], ahi[r][1], alo[r][1]);
-      split_tf32(src[o1 + m], ahi[r][2], alo[r][2]);
-      split_tf32(src[o1 + m + 8], ahi[r][3], alo[r][3]);
+      split_tf32x2(src[o0 + m], src[o0 + m + 8], ahi[r][0], ahi[r][1], alo[r][0], alo[r][1]);
+      split_tf32x2(src[o1 + m], src[o1 + m + 8], ahi[r][2], ahi[r][3], alo[r][2], alo[r][3]);
     }
 #pragma unroll
     for (int c = 0; c < NT; ++c) {
       const float* p = sB + (c * 8 + g) * LDB + k0 + t;
       uint32_t bhi[2], blo[2];
-      split_tf32(p[0], bhi[0], blo[0]);
-      split_tf32(p[4], bhi[1], blo[1]);
+      split_tf32x2(p[0], p[4], bhi[0], bhi[1], blo[0], blo[1]);
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         mma_tf32(acc[r][c], alo[r], bhi);
@@ -212,12 +209,9 @@ __global__ void __launch_bounds__(RL_NT) conv13_bwd_mma_kernel(const rl_conv_bwd
       const int ob = s.offA[nt * 8 + g];                    // B(k = t', n = (i,k)) = x[i][t' + k]
       for (int k0 = 0; k0 < L; k0 += 8) {
         uint32_t ahi[4], alo[4], bhi[2], blo[2];
-        split_tf32(s.sdc[g * LP + PAD + k0 + t], ahi[0], alo[0]);
-        split_tf32(s.sdc[(g + 8) * LP + PAD + k0 + t], ahi[1], alo[1]);
-        split_tf32(s.sdc[g * LP + PAD + k0 + t + 4], ahi[2], alo[2]);
-        split_tf32(s.sdc[(g + 8) * LP + PAD + k0 + t + 4], ahi[3], alo[3]);
-        split_tf32(s.sx[ob + k0 + t], bhi[0], blo[0]);
-        split_tf32(s.sx[ob + k0 + t + 4], bhi[1], blo[1]);
+        split_tf32x2(s.sdc[g * LP + PAD + k0 + t], s.sdc[(g + 8) * LP + PAD + k0 + t], ahi[0], ahi[1], alo[0], alo[1]);
+        split_tf32x2(s.sdc[g * LP + PAD + k0 + t + 4], s.sdc[(g + 8) * LP + PAD + k0 + t + 4], ahi[2], ahi[3], alo[2], alo[3]);
+        split_tf32x2(s.sx[ob + k0 + t], s.sx[ob + k0 + t + 4], bhi[0], bhi[1], blo[0], blo[1]);
         mma_tf32(acc, alo, bhi);
         mma_tf32(acc, ahi, blo);
         mma_tf32(acc, ahi, bhi);

@@ -88,8 +88,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
     float4* lo4 = reinterpret_cast<float4*>(sB + b * 2 * FwdSmem<C>::B_FLOATS + FwdSmem<C>::B_FLOATS);
     for (int i = threadIdx.x; i < rows * KC / 4; i += RL_NT) {
       const float4 v = hi4[i];
-      lo4[i] = make_float4(v.x - umma::trunc_tf32(v.x), v.y - umma::trunc_tf32(v.y), v.z - umma::trunc_tf32(v.z),
-                           v.w - umma::trunc_tf32(v.w));
+      lo4[i] = umma::lo4(v);
     }
   };
   if (threadIdx.x == 0) {
@@ -175,8 +174,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
       }
       const int o = rsub * 4 + qc * 32 + warp * (C / 4) * 32;
       *reinterpret_cast<float4*>(sA_hi + o) = u;
-      *reinterpret_cast<float4*>(sA_lo + o) = make_float4(u.x - umma::trunc_tf32(u.x), u.y - umma::trunc_tf32(u.y),
-                                                          u.z - umma::trunc_tf32(u.z), u.w - umma::trunc_tf32(u.w));
+      *reinterpret_cast<float4*>(sA_lo + o) = umma::lo4(u);
     }
   }
   umma::tc_fence_before();
@@ -283,8 +281,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
       const int o = obase + (col0 / 4 + i) * 32;
       const float4 g = make_float4(hv[4 * i], hv[4 * i + 1], hv[4 * i + 2], hv[4 * i + 3]);
       *reinterpret_cast<float4*>(sA_hi + o) = g;
-      *reinterpret_cast<float4*>(sA_lo + o) = make_float4(g.x - umma::trunc_tf32(g.x), g.y - umma::trunc_tf32(g.y),
-                                                          g.z - umma::trunc_tf32(g.z), g.w - umma::trunc_tf32(g.w));
+      *reinterpret_cast<float4*>(sA_lo + o) = umma::lo4(g);
     }
   }
   umma::tc_fence_before();     // the tcgen05.ld reads of the fc1 accumulator precede the barrier below
@@ -473,8 +470,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_umma_kernel(const rl_f
                           : make_float4(0.f, 0.f, 0.f, 0.f);
       const int o = rsub * 4 + qc * 32 + warp * (C / 4) * 32;
       *reinterpret_cast<float4*>(sA_hi + o) = v;
-      *reinterpret_cast<float4*>(sA_lo + o) = make_float4(v.x - umma::trunc_tf32(v.x), v.y - umma::trunc_tf32(v.y),
-                                                          v.z - umma::trunc_tf32(v.z), v.w - umma::trunc_tf32(v.w));
+      *reinterpret_cast<float4*>(sA_lo + o) = umma::lo4(v);
     }
   }
   umma::tc_fence_before();
@@ -580,8 +576,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_umma_kernel(const rl_f
         const int o = obase + (col0 / 4 + 4 * half + i) * 32;
         const float4 d = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         *reinterpret_cast<float4*>(sA_hi + o) = d;
-        *reinterpret_cast<float4*>(sA_lo + o) = make_float4(d.x - umma::trunc_tf32(d.x), d.y - umma::trunc_tf32(d.y),
-                                                            d.z - umma::trunc_tf32(d.z), d.w - umma::trunc_tf32(d.w));
+        *reinterpret_cast<float4*>(sA_lo + o) = umma::lo4(d);
       }
     }
     __syncthreads();

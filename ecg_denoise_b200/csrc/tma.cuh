@@ -76,8 +76,7 @@ __device__ __forceinline__ void derive_lo(const float* hi, float* lo, int floats
   float4* l4 = reinterpret_cast<float4*>(lo);
   for (int i = threadIdx.x; i < floats / 4; i += NT) {
     const float4 v = h4[i];
-    l4[i] = make_float4(v.x - umma::trunc_tf32(v.x), v.y - umma::trunc_tf32(v.y), v.z - umma::trunc_tf32(v.z),
-                        v.w - umma::trunc_tf32(v.w));
+    l4[i] = umma::lo4(v);
   }
 }
 }  // namespace tma

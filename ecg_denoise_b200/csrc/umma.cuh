@@ -142,6 +142,20 @@ __device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int col) {
 }
 
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// tf32 remainder of four values, v - trunc_tf32(v), with two packed subtractions (Blackwell `sub.f32x2`, SASS FADD2)
+__device__ __forceinline__ float4 lo4(float4 v) {
+  const float t0 = trunc_tf32(v.x), t1 = trunc_tf32(v.y), t2 = trunc_tf32(v.z), t3 = trunc_tf32(v.w);
+  float4 r;
+  asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tsub.f32x2 c, a, b;\n\t"
+      "mov.b64 {%0, %1}, c;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(v.x), "f"(v.y), "f"(t0), "f"(t1));
+  asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tsub.f32x2 c, a, b;\n\t"
+      "mov.b64 {%0, %1}, c;\n\t}"
+      : "=f"(r.z), "=f"(r.w)
+      : "f"(v.z), "f"(v.w), "f"(t2), "f"(t3));
+  return r;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Staging of a ROWS x KC operand block from a k-contiguous global matrix into a K-major tile pair
@@ -180,8 +194,7 @@ struct KStage {
         const int rgrp = grp % RG, qgrp = grp / RG;
         const int o = rsub * 4 + (qgrp * 4 + qsub) * 32 + rgrp * (NCH * 32);
         *reinterpret_cast<float4*>(hi + o) = v[i];
-        *reinterpret_cast<float4*>(lo + o) = make_float4(v[i].x - trunc_tf32(v[i].x), v[i].y - trunc_tf32(v[i].y),
-                                                         v[i].z - trunc_tf32(v[i].z), v[i].w - trunc_tf32(v[i].w));
+        *reinterpret_cast<float4*>(lo + o) = lo4(v[i]);
       }
     }
   }
@@ -221,8 +234,7 @@ struct TStage {
         const int n = nb * 32 + lane;
         const int o = (n & 7) * 4 + q * 32 + (n >> 3) * (NQ * 32);
         *reinterpret_cast<float4*>(hi + o) = v[i];
-        *reinterpret_cast<float4*>(lo + o) = make_float4(v[i].x - trunc_tf32(v[i].x), v[i].y - trunc_tf32(v[i].y),
-                                                         v[i].z - trunc_tf32(v[i].z), v[i].w - trunc_tf32(v[i].w));
+        *reinterpret_cast<float4*>(lo + o) = lo4(v[i]);
       }
     }
   }

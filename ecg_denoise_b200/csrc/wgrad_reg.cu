@@ -100,15 +100,12 @@ __global__ void __launch_bounds__(RL_NT, 2) wgrad_reg_kernel(const RgGroup grp) 
       uint32_t ahi[2][4], alo[2][4], bhi[4][2], blo[4][2];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        split_tf32(av0[2 * i], ahi[i][0], alo[i][0]);
-        split_tf32(av0[2 * i + 1], ahi[i][1], alo[i][1]);
-        split_tf32(av1[2 * i], ahi[i][2], alo[i][2]);
-        split_tf32(av1[2 * i + 1], ahi[i][3], alo[i][3]);
+        split_tf32x2(av0[2 * i], av0[2 * i + 1], ahi[i][0], ahi[i][1], alo[i][0], alo[i][1]);
+        split_tf32x2(av1[2 * i], av1[2 * i + 1], ahi[i][2], ahi[i][3], alo[i][2], alo[i][3]);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {             // n8 tile j holds output column k0 + 4 g + j as its fragment column g
-        split_tf32(bv0[j], bhi[j][0], blo[j][0]);
-        split_tf32(bv1[j], bhi[j][1], blo[j][1]);
+        split_tf32x2(bv0[j], bv1[j], bhi[j][0], bhi[j][1], blo[j][0], blo[j][1]);
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i)

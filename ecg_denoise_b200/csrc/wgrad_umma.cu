@@ -90,8 +90,7 @@ struct TokStage {
         const int o = (n & 7) * 4 + q * 32 + (n >> 3) * (NQ * 32);
         *reinterpret_cast<float4*>(hi + o) = v[i];
         *reinterpret_cast<float4*>(lo + o) =
-            make_float4(v[i].x - umma::trunc_tf32(v[i].x), v[i].y - umma::trunc_tf32(v[i].y),
-                        v[i].z - umma::trunc_tf32(v[i].z), v[i].w - umma::trunc_tf32(v[i].w));
+            umma::lo4(v[i]);
       }
     }
   }

@@ -84,15 +84,20 @@ __device__ __forceinline__ void attn_core_fwd_item(float* sq, const float* sk, c
     x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
     const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);
     const float r0 = fast_ex2(m0 - n0), r1 = fast_ex2(m1 - n1);
-    l0 *= r0; l1 *= r1;
-    o[0] *= r0; o[1] *= r0; o[2] *= r1; o[3] *= r1;
+    // (packed fp32 arithmetic: same operations and rounding as the scalar form, half the issue slots)
+    mul_f32x2(l0, l1, r0, r1, l0, l1);
+    mul_f32x2(o[0], o[1], r0, r0, o[0], o[1]);
+    mul_f32x2(o[2], o[3], r1, r1, o[2], o[3]);
     m0 = n0; m1 = n1;
 #pragma unroll
     for (int tt = 0; tt < CH; ++tt) {
-      const float p0 = fast_ex2(s[tt][0] - n0), p1 = fast_ex2(s[tt][1] - n0);
-      const float p2 = fast_ex2(s[tt][2] - n1), p3 = fast_ex2(s[tt][3] - n1);
-      l0 += p0 + p1;
-      l1 += p2 + p3;
+      float d0, d1, d2, d3;
+      sub_f32x2(s[tt][0], s[tt][1], n0, n0, d0, d1);
+      sub_f32x2(s[tt][2], s[tt][3], n1, n1, d2, d3);
+      const float p0 = fast_ex2(d0), p1 = fast_ex2(d1), p2 = fast_ex2(d2), p3 = fast_ex2(d3);
+      float q0, q1;
+      add_f32x2(p0, p2, p1, p3, q0, q1);          // (p0 + p1, p2 + p3)
+      add_f32x2(l0, l1, q0, q1, l0, l1);
       uint32_t ah[4], al[4];
       split_tf32x2(p0, p2, ah[0], ah[1], al[0], al[1]);
       split_tf32x2(p1, p3, ah[2], ah[3], al[2], al[3]);
@@ -171,7 +176,9 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
 // (x0, x1) -> packed fp16 pairs hi = (fp16(x0), fp16(x1)), lo = the fp16 remainders; x0 in the low half
 __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x0, x1);
-  const __half2 l = __floats2half2_rn(x0 - __low2float(h), x1 - __high2float(h));
+  float r0, r1;
+  sub_f32x2(x0, x1, __low2float(h), __high2float(h), r0, r1);
+  const __half2 l = __floats2half2_rn(r0, r1);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -258,10 +265,9 @@ __device__ __forceinline__ void attn_core_bwd_single(const float* QPf, const flo
         }
         float p[4], ds[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          p[e] = fast_ex2(s[e]);
-          ds[e] = p[e] * dp[e];
-        }
+        for (int e = 0; e < 4; ++e) p[e] = fast_ex2(s[e]);
+        mul_f32x2(p[0], p[1], dp[0], dp[1], ds[0], ds[1]);
+        mul_f32x2(p[2], p[3], dp[2], dp[3], ds[2], ds[3]);
         if (cen && want_tab) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {

@@ -126,6 +126,56 @@ __device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
   dg = fmaf(x * e, 0.3989422804014327f, cdf);
 }
 
+// ---- two GELUs at once on Blackwell's packed fp32 pipe (FMUL2 / FFMA2 / FADD2): same arithmetic, same bits, as two
+// gelu_parts() calls, two thirds of the issue slots.  GELU and GELU' are ~15 % of all instructions of a training step
+// (2 + 2 evaluations per hidden element and block).
+__device__ __forceinline__ void pk_mul(float x0, float x1, float y0, float y1, float& r0, float& r1) {
+  asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmul.f32x2 c, a, b;\n\t"
+      "mov.b64 {%0, %1}, c;\n\t}"
+      : "=f"(r0), "=f"(r1)
+      : "f"(x0), "f"(x1), "f"(y0), "f"(y1));
+}
+__device__ __forceinline__ void pk_fma(float x0, float x1, float y0, float y1, float z0, float z1, float& r0, float& r1) {
+  asm("{\n\t.reg .b64 a, b, c, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%6, %7};\n\t"
+      "fma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(r0), "=f"(r1)
+      : "f"(x0), "f"(x1), "f"(y0), "f"(y1), "f"(z0), "f"(z1));
+}
+__device__ __forceinline__ void gelu_parts2(float x0, float x1, float& cdf0, float& cdf1, float& g0, float& g1) {
+  float z0, z1, u0, u1, t0, t1, s0, s1, e0, e1, q0, q1;
+  pk_mul(fabsf(x0), fabsf(x1), 0.70710678118654752f, 0.70710678118654752f, z0, z1);
+  pk_fma(z0, z1, 0.3275911f, 0.3275911f, 1.0f, 1.0f, u0, u1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  pk_mul(x0, x1, x0, x1, s0, s1);
+  pk_mul(s0, s1, -0.72134752044448170f, -0.72134752044448170f, s0, s1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1));
+  pk_fma(t0, t1, 0.5f * 1.061405429f, 0.5f * 1.061405429f, 0.5f * -1.453152027f, 0.5f * -1.453152027f, q0, q1);
+  pk_fma(q0, q1, t0, t1, 0.5f * 1.421413741f, 0.5f * 1.421413741f, q0, q1);
+  pk_fma(q0, q1, t0, t1, 0.5f * -0.284496736f, 0.5f * -0.284496736f, q0, q1);
+  pk_fma(q0, q1, t0, t1, 0.5f * 0.254829592f, 0.5f * 0.254829592f, q0, q1);
+  pk_mul(q0, q1, t0, t1, q0, q1);
+  pk_mul(q0, q1, e0, e1, q0, q1);
+  cdf0 = (x0 < 0.f) ? q0 : 1.0f - q0;
+  cdf1 = (x1 < 0.f) ? q1 : 1.0f - q1;
+  g0 = e0;
+  g1 = e1;
+}
+__device__ __forceinline__ void gelu2(float x0, float x1, float& y0, float& y1) {
+  float c0, c1, e0, e1;
+  gelu_parts2(x0, x1, c0, c1, e0, e1);
+  pk_mul(x0, x1, c0, c1, y0, y1);
+}
+// gelu and gelu' of two values sharing one evaluation each
+__device__ __forceinline__ void gelu_both2(float x0, float x1, float& g0, float& g1, float& d0, float& d1) {
+  float c0, c1, e0, e1, w0, w1;
+  gelu_parts2(x0, x1, c0, c1, e0, e1);
+  pk_mul(x0, x1, c0, c1, g0, g1);
+  pk_mul(x0, x1, e0, e1, w0, w1);
+  pk_fma(w0, w1, 0.3989422804014327f, 0.3989422804014327f, c0, c1, d0, d1);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -378,6 +428,25 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
+// Blackwell packed fp32 arithmetic on register pairs (SASS FADD2 / FMUL2): one issue slot for two lanes of work
+__device__ __forceinline__ void sub_f32x2(float x0, float x1, float y0, float y1, float& r0, float& r1) {
+  asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tsub.f32x2 c, a, b;\n\t"
+      "mov.b64 {%0, %1}, c;\n\t}"
+      : "=f"(r0), "=f"(r1)
+      : "f"(x0), "f"(x1), "f"(y0), "f"(y1));
+}
+__device__ __forceinline__ void add_f32x2(float x0, float x1, float y0, float y1, float& r0, float& r1) {
+  asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tadd.f32x2 c, a, b;\n\t"
+      "mov.b64 {%0, %1}, c;\n\t}"
+      : "=f"(r0), "=f"(r1)
+      : "f"(x0), "f"(x1), "f"(y0), "f"(y1));
+}
+__device__ __forceinline__ void mul_f32x2(float x0, float x1, float y0, float y1, float& r0, float& r1) {
+  asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmul.f32x2 c, a, b;\n\t"
+      "mov.b64 {%0, %1}, c;\n\t}"
+      : "=f"(r0), "=f"(r1)
+      : "f"(x0), "f"(x1), "f"(y0), "f"(y1));
+}
 // two splits at once: the remainders come from ONE packed subtraction (Blackwell `sub.f32x2`, SASS FADD2) -- the split
 // arithmetic is 18 % of the instructions of the narrow-stage GEMM kernels (ncu r2_v24), this takes a quarter of it out
 __device__ __forceinline__ void split_tf32x2(float x0, float x1, uint32_t& h0, uint32_t& h1, uint32_t& l0, uint32_t& l1) {
@@ -495,6 +564,32 @@ struct MmaTile {
         f(m, n + 1, acc[r][c][1], v[r][c][1]);
         f(m + 8, n, acc[r][c][2], v[r][c][2]);
         f(m + 8, n + 1, acc[r][c][3], v[r][c][3]);
+      }
+  }
+
+  // pairs of adjacent columns: f(row, col, v0, v1) resp. f(row, col, v0, v1, gathered0, gathered1); col is even
+  template <class F>
+  __device__ __forceinline__ void epilogue_pairs(F f) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const int m = row0 + r * 16 + g, n = col0 + c * 8 + 2 * t;
+        f(m, n, acc[r][c][0], acc[r][c][1]);
+        f(m + 8, n, acc[r][c][2], acc[r][c][3]);
+      }
+  }
+  template <class F>
+  __device__ __forceinline__ void epilogue2_pairs(const float (&v)[RT][CT][4], F f) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const int m = row0 + r * 16 + g, n = col0 + c * 8 + 2 * t;
+        f(m, n, acc[r][c][0], acc[r][c][1], v[r][c][0], v[r][c][1]);
+        f(m + 8, n, acc[r][c][2], acc[r][c][3], v[r][c][2], v[r][c][3]);
       }
   }
 

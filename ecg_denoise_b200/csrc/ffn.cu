@@ -116,36 +116,45 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
     constexpr bool BATCH = MmaTile<L, HC>::TPW * 4 <= 16;
     float hv[MmaTile<L, HC>::RT][MmaTile<L, HC>::CT][4];
     if (!DW && BATCH) acc.gather(hw, HC, hv);
-    acc.epilogue2(hv, [&](int t, int n, float v, float hval) {
-      if (DW) {
+    if (DW) {
+      acc.epilogue2(hv, [&](int t, int n, float v, float hval) {
         const float g1 = sh[t * LDH + n];
         const float p = (t > 0) ? sh[(t - 1) * LDH + n] : 0.f;
         const float nx = (t + 1 < L) ? sh[(t + 1) * LDH + n] : 0.f;
         const float f = __ldg(a.lew + 3 * n) * p + __ldg(a.lew + 3 * n + 1) * g1 + __ldg(a.lew + 3 * n + 2) * nx;
         sd[t * LDH + n] = v * gelu_grad_f(f);          // df, finished below
-      } else {
-        float g1, d1;
-        gelu_both(BATCH ? hval : __ldg(hw + t * HC + n), g1, d1);
+      });
+    } else {
+      // two adjacent hidden units per call: GELU / GELU' of both on the packed fp32 pipe (gelu_both2)
+      acc.epilogue2_pairs(hv, [&](int t, int n, float v0, float v1, float h0, float h1) {
+        if (!BATCH) { h0 = __ldg(hw + t * HC + n); h1 = __ldg(hw + t * HC + n + 1); }
+        float g1[2], d1[2];
+        gelu_both2(h0, h1, g1[0], g1[1], d1[0], d1[1]);
+        float g2[2], dh[2];
         if (mode == RL_LE_NONE) {
-          if (FW) sg2[t * LDH + n] = g1; else g2w[t * HC + n] = g1;
-          const float dh = v * d1;
-          sd[t * LDH + n] = dh;
-          if (!FW) dhw[t * HC + n] = dh;
-        } else if (n == 0) {                           // partial, convolved channel: finish after the FIR adjoint
-          float g2, d2;
-          gelu_both(sf0[t], g2, d2);
-          if (FW) sg2[t * LDH] = g2; else g2w[t * HC] = g2;
-          sdf0[t] = v * d2;
-        } else {                                       // partial, untouched channel: f == g1
-          float g2, d2;
-          gelu_both(g1, g2, d2);
-          if (FW) sg2[t * LDH + n] = g2; else g2w[t * HC + n] = g2;
-          const float dh = v * d2 * d1;
-          sd[t * LDH + n] = dh;
-          if (!FW) dhw[t * HC + n] = dh;
+          g2[0] = g1[0]; g2[1] = g1[1];
+          dh[0] = v0 * d1[0]; dh[1] = v1 * d1[1];
+        } else {
+          // partial: the convolved channel (n == 0) takes the FIR output and is finished after the FIR adjoint,
+          // the untouched channels have f == g1
+          const bool conv0 = (n == 0);
+          float d2[2];
+          gelu_both2(conv0 ? sf0[t] : g1[0], g1[1], g2[0], g2[1], d2[0], d2[1]);
+          if (conv0) sdf0[t] = v0 * d2[0];
+          dh[0] = conv0 ? 0.f : v0 * d2[0] * d1[0];
+          dh[1] = v1 * d2[1] * d1[1];
         }
-      }
-    });
+        if (FW) *reinterpret_cast<float2*>(sg2 + t * LDH + n) = make_float2(g2[0], g2[1]);
+        else *reinterpret_cast<float2*>(g2w + t * HC + n) = make_float2(g2[0], g2[1]);
+        if (mode != RL_LE_NONE && n == 0) {            // (the old code left sd / dh of the convolved channel untouched)
+          sd[t * LDH + 1] = dh[1];
+          if (!FW) dhw[t * HC + 1] = dh[1];
+        } else {
+          *reinterpret_cast<float2*>(sd + t * LDH + n) = make_float2(dh[0], dh[1]);
+          if (!FW) *reinterpret_cast<float2*>(dhw + t * HC + n) = make_float2(dh[0], dh[1]);
+        }
+      });
+    }
     __syncthreads();
     if (!DW && mode == RL_LE_PARTIAL) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f;

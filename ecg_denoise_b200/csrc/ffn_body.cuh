@@ -54,10 +54,12 @@ __device__ __forceinline__ void ffn_fwd_body(const rl_ffn_fwd_args& a, float* sm
     WStream<C, HC, B_NK>::prefetch(sw, a.w2, C, nullptr, HC);      // lands behind the GELU / local-enhancement phase
     const float* b1 = a.b1;
     float* hs = a.h ? a.h + (size_t)blockIdx.x * L * HC : nullptr;
-    acc.epilogue([&](int t, int n, float v) {
-      v += b1 ? __ldg(b1 + n) : 0.f;
-      if (hs) hs[t * HC + n] = v;
-      sh[t * LDH + n] = gelu_f(v);
+    acc.epilogue_pairs([&](int t, int n, float v0, float v1) {      // two hidden units per call: packed-fp32 GELU
+      if (b1) { v0 += __ldg(b1 + n); v1 += __ldg(b1 + n + 1); }
+      if (hs) *reinterpret_cast<float2*>(hs + t * HC + n) = make_float2(v0, v1);
+      float g0, g1;
+      gelu2(v0, v1, g0, g1);
+      *reinterpret_cast<float2*>(sh + t * LDH + n) = make_float2(g0, g1);
     });
   }
   __syncthreads();
@@ -71,10 +73,12 @@ __device__ __forceinline__ void ffn_fwd_body(const rl_ffn_fwd_args& a, float* sm
       sfir[t] = w0 * p + w1 * sh[t * LDH] + w2 * n;
     }
     __syncthreads();
-    for (int i = tid; i < L * HC; i += RL_NT) {
-      const int t = i / HC, n = i % HC;
-      const float f = (n == 0) ? sfir[t] : sh[t * LDH + n];
-      sh[t * LDH + n] = gelu_f(f);
+    for (int i = tid; i < L * HC / 2; i += RL_NT) {        // two hidden units at a time on the packed fp32 pipe
+      const int t = (2 * i) / HC, n = (2 * i) % HC;
+      float2 f = *reinterpret_cast<const float2*>(sh + t * LDH + n);
+      if (n == 0) f.x = sfir[t];
+      gelu2(f.x, f.y, f.x, f.y);
+      *reinterpret_cast<float2*>(sh + t * LDH + n) = f;
     }
     __syncthreads();
   } else if (a.le_mode == RL_LE_DEPTHWISE) {

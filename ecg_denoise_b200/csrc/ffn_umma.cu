@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
       for (int i = 0; i < 8; ++i) hs[i] = make_float4(hv[4 * i], hv[4 * i + 1], hv[4 * i + 2], hv[4 * i + 3]);
     }
 #pragma unroll
-    for (int i = 0; i < 32; ++i) hv[i] = gelu_f(hv[i]);
+    for (int i = 0; i < 32; i += 2) gelu2(hv[i], hv[i + 1], hv[i], hv[i + 1]);
     const bool own0 = part && r == 0 && cgp == 0;            // this thread holds hidden channel 0 of its row
     if (own0) sg10[row] = hv[0];
     __syncthreads();
@@ -267,13 +267,10 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_umma_kernel(const rl_f
         const float w0f = __ldg(a.lew), w1f = __ldg(a.lew + 1), w2f = __ldg(a.lew + 2);
         const float p = (tl > 0) ? sg10[row - 1] : 0.f;
         const float n = (tl + 1 < L) ? sg10[row + 1] : 0.f;
-        hv[0] = gelu_f(w0f * p + w1f * hv[0] + w2f * n);
-#pragma unroll
-        for (int i = 1; i < 32; ++i) hv[i] = gelu_f(hv[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) hv[i] = gelu_f(hv[i]);
+        hv[0] = w0f * p + w1f * hv[0] + w2f * n;
       }
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) gelu2(hv[i], hv[i + 1], hv[i], hv[i + 1]);
     }
     const int obase = (row & 7) * 4 + (row >> 3) * (TS / 4) * 32;
 #pragma unroll
@@ -543,23 +540,25 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_umma_kernel(const rl_f
         hh[4 * i] = t4.x; hh[4 * i + 1] = t4.y; hh[4 * i + 2] = t4.z; hh[4 * i + 3] = t4.w;
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float g1, d1;
-        gelu_both(hh[i], g1, d1);
+      for (int i = 0; i < 16; i += 2) {                      // two hidden units at a time on the packed fp32 pipe
+        float g1[2], d1[2];
+        gelu_both2(hh[i], hh[i + 1], g1[0], g1[1], d1[0], d1[1]);
         if (mode == RL_LE_NONE) {
-          g2v[i] = g1;
-          v[i] *= d1;
-        } else if (own0 && half == 0 && i == 0) {            // convolved channel: finished after the FIR adjoint
-          float g2, d2;
-          gelu_both(f0, g2, d2);
-          g2v[i] = g2;
-          sdf0[row] = v[i] * d2;
-          v[i] = 0.f;
-        } else {                                             // untouched channel: f == g1
-          float g2, d2;
-          gelu_both(g1, g2, d2);
-          g2v[i] = g2;
-          v[i] *= d2 * d1;
+          g2v[i] = g1[0]; g2v[i + 1] = g1[1];
+          v[i] *= d1[0]; v[i + 1] *= d1[1];
+        } else {
+          // second GELU: the convolved channel (column 0 of slice 0) takes the FIR output, the others f == g1
+          const bool conv0 = own0 && half == 0 && i == 0;
+          float g2[2], d2[2];
+          gelu_both2(conv0 ? f0 : g1[0], g1[1], g2[0], g2[1], d2[0], d2[1]);
+          g2v[i] = g2[0]; g2v[i + 1] = g2[1];
+          if (conv0) {                                       // finished after the FIR adjoint
+            sdf0[row] = v[i] * d2[0];
+            v[i] = 0.f;
+          } else {
+            v[i] *= d2[0] * d1[0];
+          }
+          v[i + 1] *= d2[1] * d1[1];
         }
       }
       if (ok) {

@@ -187,7 +187,6 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   float* sw = sLse + LC / 4;
   float* stab = sw + attn_bwd_swf<C>();
   float* stabg = stab + 128;
-  float* s_gb = stabg + 128;
   const int tid = threadIdx.x;
   RL_TS(attn, 0);
   const size_t woff = (size_t)blockIdx.x * LC;
@@ -221,7 +220,6 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
     stabg[tid] = 0.f;
     stab[tid] = (W > 0 && tid < (2 * W - 1) * H) ? __ldg(a.table + tid) * RL_LOG2E : 0.f;
   }
-  for (int i = tid; i < 2 * C; i += RL_NT) s_gb[i] = 0.f;
   __syncthreads();
   RL_TS(attn, 2);
 
@@ -260,8 +258,12 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   __syncthreads();
 
   constexpr bool FW = (C <= RL_FW_MAXC);   // narrow stages: weight gradients are accumulated in-CTA (no wgrad launch)
-  if (FW) cta_wgrad_mma<C, C, L>(sdq, LDC, sdk, LDC, a.d_wp, a.d_bp, 0);          // dWp = g^T o,  dbp = sum g
-  if (FW) __syncthreads();
+  if constexpr (FW) {                      // dWp = g^T o,  dbp = sum g; su is free until step 6
+    static_assert(CtaWgrad<C, C, L>::SCRATCH <= LP, "attn_bwd: scratch");
+    CtaWgrad<C, C, L>::partial(sdq, LDC, sdk, LDC, su);
+    __syncthreads();
+    CtaWgrad<C, C, L>::reduce(su, a.d_wp, a.d_bp);
+  }
   RL_TS(attn, 4);
 
   // 4. attention core backward on the tensor cores (attn_core.cuh), single pass: q, k, v, do are re-packed in place
@@ -311,8 +313,9 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
     const float* pe = a.pe;
     const float* lw = a.ln_w;
     const float* lb = a.ln_b;
-    ln_backward_rows<C>(
-        L, lw, s_gb, [&](int t, int c) { return fmaf(__ldg(xw + t * C + c), sc, __ldg(pe + t * C + c)); },
+    // per-warp partial rows of the LayerNorm weight / bias gradients go to sq..sk (16 x 2C floats; q, k are dead)
+    ln_backward_rows<C, true>(
+        L, lw, sq, [&](int t, int c) { return fmaf(__ldg(xw + t * C + c), sc, __ldg(pe + t * C + c)); },
         [&](int t, int c) { return su[t * LDC + c]; },
         [&](int t, int c, float dz, float zh) {
           dxw[t * C + c] = (resid ? __ldg(gw + t * C + c) : 0.f) + sc * dz;
@@ -320,11 +323,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
           if (FW) su[t * LDC + c] = u; else uw[t * C + c] = u;      // du at (t, c) was consumed by this thread
         });
     __syncthreads();
-    if (a.d_ln_w)
-      for (int i = tid; i < C; i += RL_NT) {
-        atomicAdd(a.d_ln_w + i, s_gb[i]);
-        atomicAdd(a.d_ln_b + i, s_gb[C + i]);
-      }
+    ln_backward_finish<C>(sq, a.d_ln_w, a.d_ln_b);
   } else {
     for (int i = tid; i < LC; i += RL_NT) {
       const int t = i / C, c = i % C;
@@ -334,10 +333,16 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
     __syncthreads();
   }
   RL_TS(attn, 9);
-  if (FW) {   // dWq = dq^T u, dWkv = [dk | dv]^T u  (u now sits in su)
-    cta_wgrad_mma<C, C, L>(sdq, LDC, su, LDC, a.d_wq, a.d_bq, 0);
-    cta_wgrad_mma<C, C, L>(sdk, LDC, su, LDC, a.d_wkv, a.d_bkv, 5);
-    cta_wgrad_mma<C, C, L>(sdv, LDC, su, LDC, a.d_wkv ? a.d_wkv + C * C : nullptr, a.d_bkv ? a.d_bkv + C : nullptr, 10);
+  if constexpr (FW) {   // dWq = dq^T u, dWkv = [dk | dv]^T u  (u now sits in su); scratch: sk, sv, sdo (dead since the core)
+    using WG = CtaWgrad<C, C, L>;
+    static_assert(WG::SCRATCH <= LP && 16 * 2 * C <= LP, "attn_bwd: scratch regions");
+    WG::partial(sdq, LDC, su, LDC, sk);
+    WG::partial(sdk, LDC, su, LDC, sv);
+    WG::partial(sdv, LDC, su, LDC, sdo);
+    __syncthreads();
+    WG::reduce(sk, a.d_wq, a.d_bq);
+    WG::reduce(sv, a.d_wkv, a.d_bkv);
+    WG::reduce(sdo, a.d_wkv ? a.d_wkv + C * C : nullptr, a.d_bkv ? a.d_bkv + C : nullptr);
   }
   if (a.d_table && W > 0)
     for (int i = tid; i < (2 * W - 1) * H; i += RL_NT) atomicAdd(a.d_table + i, stabg[i]);

@@ -300,7 +300,10 @@ __device__ __forceinline__ void ln_forward_rows(int rows, Load load, Store store
 //   loadz(t,c): pre-norm input;  loaddu(t,c): gradient w.r.t. LN output;  gamma: [C]
 //   emit(t, c, dz, zhat): receives the gradient w.r.t. the pre-norm input and zhat
 //   dgam/dbet partial sums are accumulated into s_gb[0:C] / s_gb[C:2C] (shared, pre-zeroed) with atomics.
-template <int C, class LoadZ, class LoadDu, class Emit>
+//   WP = true: s_gb is [RL_NT/32][2C], one row of partial sums per WARP written with plain stores (no pre-zeroing, no
+//   shared-memory atomics: those are compare-and-swap loops for fp32 and 16 warps x TPW token groups contend for every
+//   word -- 8 % of the samples of the narrow backward kernels, ncu r2_v32); ln_backward_finish() adds the rows up.
+template <int C, bool WP = false, class LoadZ, class LoadDu, class Emit>
 __device__ __forceinline__ void ln_backward_rows(int rows, const float* __restrict__ gamma, float* s_gb, LoadZ loadz,
                                                  LoadDu loaddu, Emit emit) {
   using G = LnGeom<C>;
@@ -350,12 +353,37 @@ __device__ __forceinline__ void ln_backward_rows(int rows, const float* __restri
       for (int i = 0; i < G::CPL; ++i) emit(t, gl + i * G::GS, rstd * (du[i] - s1 - z[i] * s2), z[i]);
     }
   }
-  if (s_gb != nullptr) {
+  if (WP) {
+#pragma unroll
+    for (int i = 0; i < G::CPL; ++i) {
+#pragma unroll
+      for (int o = G::GS; o < 32; o <<= 1) {            // the TPW token groups of this warp hold the same channels
+        ag[i] += __shfl_xor_sync(0xffffffffu, ag[i], o);
+        ab[i] += __shfl_xor_sync(0xffffffffu, ab[i], o);
+      }
+      if (gi == 0) {
+        s_gb[warp * 2 * C + gl + i * G::GS] = ag[i];
+        s_gb[warp * 2 * C + C + gl + i * G::GS] = ab[i];
+      }
+    }
+  } else if (s_gb != nullptr) {
 #pragma unroll
     for (int i = 0; i < G::CPL; ++i) {
       atomicAdd(&s_gb[gl + i * G::GS], ag[i]);
       atomicAdd(&s_gb[C + gl + i * G::GS], ab[i]);
     }
+  }
+}
+// after a CTA barrier behind ln_backward_rows<C, true>: d_ln_w / d_ln_b += the per-warp partial rows
+template <int C>
+__device__ __forceinline__ void ln_backward_finish(const float* s_part, float* __restrict__ d_ln_w,
+                                                   float* __restrict__ d_ln_b) {
+  if (d_ln_w == nullptr) return;
+  for (int i = threadIdx.x; i < 2 * C; i += RL_NT) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < RL_NT / 32; ++w) s += s_part[w * 2 * C + i];
+    atomicAdd((i < C) ? d_ln_w + i : d_ln_b + i - C, s);
   }
 }
 
@@ -789,76 +817,80 @@ __device__ __forceinline__ void cta_wgrad(const float* A, int lda, const float* 
   }
 }
 
-// Tensor-core form of the same in-CTA weight gradient: every m16n8 tile of dW (rows = output features, padded to 16;
-// columns = input features) is owned by ONE warp, which contracts it over all L tokens with 3xTF32 MMAs
-// (A(m=n_out, k=token) = A[t*lda + n], B(k=token, n=k_in) = B[t*ldb + k]) and adds its fragment to global memory
-// once -- no cross-warp reduction.  `rot` rotates the tile -> warp assignment so that back-to-back calls (no barrier
-// between them) land on different warps.  ~6x fewer instructions than the FMA form above.
+// Tensor-core form of the same in-CTA weight gradient, in two phases around ONE CTA barrier:
+//   partial(): every warp owns one (m16n8 tile of dW, token range) item -- rows = output features (padded to 16),
+//     columns = input features, the L tokens split KS ways so that all 16 warps work (round 2 gave each tile to one warp
+//     for all L tokens: at C = 16 two warps ran the MMAs while fourteen sat at the next barrier, 15 % of the samples of
+//     attn_bwd<16> and 13 % of ffn_bwd<16> in ncu r2_v32) -- contracts it with 3xTF32 MMAs
+//     (A(m = n_out, k = token) = A[t*lda + n], B(k = token, n = k_in) = B[t*ldb + k]) and leaves its fragment in
+//     `scratch`; the warps of the first column tile also sum their A fragments over the tokens: the bias gradient.
+//   reduce(): (after the barrier) adds the KS fragments of every element and issues one red.global per element of dW /
+//     db and CTA.  No shared-memory atomics anywhere.
+// Several partial()s into different scratch regions can share the barrier.
 template <int N, int K, int L>
-__device__ __forceinline__ void cta_wgrad_mma(const float* A, int lda, const float* B, int ldb, float* __restrict__ dW,
-                                              float* __restrict__ db, int rot) {
-  static_assert(K % 8 == 0 && L % 8 == 0, "cta_wgrad_mma: K and L must be multiples of 8");
-  constexpr int MT = (N + 15) / 16, NT = K / 8, NW = RL_NT / 32, TILES = MT * NT;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  if (dW != nullptr) {
-    for (int tile = (warp + NW - (rot % NW)) % NW; tile < TILES; tile += NW) {
-      const int m0 = (tile / NT) * 16, n0 = (tile % NT) * 8;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      // rows >= N of a padded tile read the neighbouring smem words (in bounds) and are never stored
-      const float* ap = A + t * lda + m0 + g;
-      const float* bp = B + t * ldb + n0 + g;
+struct CtaWgrad {
+  static_assert(K % 8 == 0, "CtaWgrad: K must be a multiple of 8");
+  static constexpr int MT = (N + 15) / 16, NT = K / 8, NW = RL_NT / 32, TILES = MT * NT;
+  static_assert(TILES <= NW && NW % TILES == 0, "CtaWgrad: the tiles must divide the warps");
+  static constexpr int KS = NW / TILES, TOK = L / KS;
+  static_assert(L % KS == 0 && TOK % 8 == 0, "CtaWgrad: token ranges must be multiples of 8");
+  static constexpr int ITEM = 144;                       // floats per item: 32 lanes x 4 + 16 column sums
+  static constexpr int SCRATCH = NW * ITEM;              // floats of scratch per call
+
+  __device__ static __forceinline__ void partial(const float* A, int lda, const float* B, int ldb, float* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int tile = warp % TILES, ks = warp / TILES;
+    const int m0 = (tile / NT) * 16, n0 = (tile % NT) * 8;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float s_lo = 0.f, s_hi = 0.f;
+    // rows >= N of a padded tile read the neighbouring smem words (in bounds) and are never stored
+    const float* ap = A + (ks * TOK + t) * lda + m0 + g;
+    const float* bp = B + (ks * TOK + t) * ldb + n0 + g;
 #pragma unroll 4
-      for (int k0 = 0; k0 < L; k0 += 8) {
-        uint32_t ahi[4], alo[4], bhi[2], blo[2];
-        split_tf32x2(ap[k0 * lda], ap[k0 * lda + 8], ahi[0], ahi[1], alo[0], alo[1]);
-        split_tf32x2(ap[(k0 + 4) * lda], ap[(k0 + 4) * lda + 8], ahi[2], ahi[3], alo[2], alo[3]);
-        split_tf32x2(bp[k0 * ldb], bp[(k0 + 4) * ldb], bhi[0], bhi[1], blo[0], blo[1]);
-        mma_tf32(acc, alo, bhi);
-        mma_tf32(acc, ahi, blo);
-        mma_tf32(acc, ahi, bhi);
-      }
-      const int m = m0 + g, n = n0 + 2 * t;
-      if (m < N) {
-        atomicAdd(dW + m * K + n, acc[0]);
-        atomicAdd(dW + m * K + n + 1, acc[1]);
-      }
-      if (m + 8 < N) {
-        atomicAdd(dW + (m + 8) * K + n, acc[2]);
-        atomicAdd(dW + (m + 8) * K + n + 1, acc[3]);
-      }
+    for (int k0 = 0; k0 < TOK; k0 += 8) {
+      const float a0 = ap[k0 * lda], a1 = ap[k0 * lda + 8], a2 = ap[(k0 + 4) * lda], a3 = ap[(k0 + 4) * lda + 8];
+      uint32_t ahi[4], alo[4], bhi[2], blo[2];
+      split_tf32x2(a0, a1, ahi[0], ahi[1], alo[0], alo[1]);
+      split_tf32x2(a2, a3, ahi[2], ahi[3], alo[2], alo[3]);
+      split_tf32x2(bp[k0 * ldb], bp[(k0 + 4) * ldb], bhi[0], bhi[1], blo[0], blo[1]);
+      mma_tf32(acc, alo, bhi);
+      mma_tf32(acc, ahi, blo);
+      mma_tf32(acc, ahi, bhi);
+      if (n0 == 0) { s_lo += a0 + a2; s_hi += a1 + a3; }
+    }
+    float* item = scratch + warp * ITEM;                   // warp = ks * TILES + tile
+    *reinterpret_cast<float4*>(item + 4 * lane) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if (n0 == 0) {                                          // warp-uniform
+      s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1);
+      s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
+      s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1);
+      s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+      if (t == 0) { item[128 + g] = s_lo; item[136 + g] = s_hi; }
     }
   }
-  if (db != nullptr) {
-    // column sums over the L tokens with the whole CTA: thread = (column, token segment); the segments of a column
-    // meet in a shared-memory word, then one global reduction per column.  (One thread per column walking all L
-    // tokens left 15 of the 16 warps waiting at the next barrier: 6.5 % of the samples of attn_bwd<16>.)
-    if constexpr (N > 64 || RL_NT % N != 0) {          // (shapes the block kernels never accumulate in-CTA)
-      if (threadIdx.x < N) {
-        float s1 = 0.f;
-        for (int tt = 0; tt < L; ++tt) s1 += A[tt * lda + threadIdx.x];
-        atomicAdd(db + threadIdx.x, s1);
-      }
-      return;
-    }
-    __shared__ float s_bsum[64];
-    constexpr int NSEG = (N <= 64 && RL_NT % N == 0) ? RL_NT / N : 1;
-    if (threadIdx.x < N) s_bsum[threadIdx.x] = 0.f;
-    __syncthreads();
-    const int c = threadIdx.x % N, seg = threadIdx.x / N;
-    float s = 0.f;
-#pragma unroll 4
-    for (int tt = seg; tt < L; tt += NSEG) s += A[tt * lda + c];
-    if (N < 32) {
+
+  __device__ static __forceinline__ void reduce(const float* scratch, float* __restrict__ dW, float* __restrict__ db) {
+    if (dW != nullptr) {
+      for (int e = threadIdx.x; e < TILES * 128; e += RL_NT) {
+        const int tile = e >> 7, idx = e & 127, ln = idx >> 2, j = idx & 3;
+        float s = 0.f;
 #pragma unroll
-      for (int o = N; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane < N) atomicAdd(&s_bsum[c], s);
-    } else {
-      atomicAdd(&s_bsum[c], s);
+        for (int ks = 0; ks < KS; ++ks) s += scratch[(ks * TILES + tile) * ITEM + idx];
+        const int m = (tile / NT) * 16 + (ln >> 2) + ((j & 2) ? 8 : 0), n = (tile % NT) * 8 + 2 * (ln & 3) + (j & 1);
+        if (m < N) atomicAdd(dW + m * K + n, s);
+      }
     }
-    __syncthreads();
-    if (threadIdx.x < N) atomicAdd(db + threadIdx.x, s_bsum[threadIdx.x]);
+    if (db != nullptr) {
+      for (int m = threadIdx.x; m < N; m += RL_NT) {
+        const int tile = (m / 16) * NT;                     // the first column tile of this row block
+        float s = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) s += scratch[(ks * TILES + tile) * ITEM + 128 + (m % 16)];
+        atomicAdd(db + m, s);
+      }
+    }
   }
-}
+};
 
 // generic weight-gradient GEMM launcher (wgrad.cu):
 //   dW[n*K + k] += sum_m dY[m*ldy + n] * X[m*ldx + k]      n < N, k < K, m < M

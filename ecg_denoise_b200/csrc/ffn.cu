@@ -33,7 +33,10 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_fwd_kernel(const rl_ffn_fw
 // epilogue of the dg2 GEMM from the saved pre-activation h (one erf shared by GELU and GELU').
 template <int C>
 __host__ __device__ constexpr int ffn_bwd_swf() {
-  return cmax(WStream<4 * C, C, B_KN>::FLOATS, WStream<C, 4 * C, B_KN>::FLOATS);
+  // also the scratch of the in-CTA weight gradients (CtaWgrad::SCRATCH = 2304 floats) and of the per-warp LayerNorm
+  // gradient partials (16 x 2C floats)
+  return cmax(cmax(WStream<4 * C, C, B_KN>::FLOATS, WStream<C, 4 * C, B_KN>::FLOATS),
+              cmax((C <= RL_FW_MAXC) ? 16 * 144 : 0, 32 * C));
 }
 template <int C>
 size_t ffn_bwd_smem(int L, bool dw) {
@@ -78,7 +81,6 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
 
   // 1. g -> sg; the pieces of g1 = GELU(h) that cross tokens
   copy_rows_g2s(sg, LDC, gw, L, C);
-  for (int i = tid; i < 2 * C; i += RL_NT) s_gb[i] = 0.f;
   float lw0 = 0.f, lw1 = 0.f, lw2 = 0.f;
   if (DW) {
     for (int i = tid; i < L * HC; i += RL_NT) sh[(i / HC) * LDH + (i % HC)] = gelu_f(__ldg(hw + i));
@@ -170,17 +172,19 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
         a1 += d * sg10[t];
         a2 += d * ((t + 1 < L) ? sg10[t + 1] : 0.f);
       }
-      if (a.d_lew) {
-        a0 = block_sum(a0, s_red);
-        a1 = block_sum(a1, s_red);
-        a2 = block_sum(a2, s_red);
-        if (tid == 0) {
-          atomicAdd(a.d_lew, a0);
-          atomicAdd(a.d_lew + 1, a1);
-          atomicAdd(a.d_lew + 2, a2);
-        }
+      if (a.d_lew) {     // the three tap gradients: per-warp sums, ONE barrier (the one below), three threads finish
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        a2 = warp_sum(a2);
+        if ((tid & 31) == 0) { s_red[3 * (tid >> 5)] = a0; s_red[3 * (tid >> 5) + 1] = a1; s_red[3 * (tid >> 5) + 2] = a2; }
       }
       __syncthreads();
+      if (a.d_lew && tid < 3) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < RL_NT / 32; ++w) s += s_red[3 * w + tid];
+        atomicAdd(a.d_lew + tid, s);
+      }
     } else if (DW) {
       for (int c = tid; c < HC; c += RL_NT) {
         const float w0 = __ldg(a.lew + 3 * c), w1 = __ldg(a.lew + 3 * c + 1), w2 = __ldg(a.lew + 3 * c + 2);
@@ -224,19 +228,17 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
   if (a.flags & RL_F_PRENORM) {
     const float* lw = a.ln_w;
     const float* lb = a.ln_b;
-    ln_backward_rows<C>(
-        L, lw, s_gb, [&](int t, int c) { return __ldg(xw + t * C + c); }, [&](int t, int c) { return su[t * LDC + c]; },
+    // per-warp partial rows of the LayerNorm weight / bias gradients go to the weight staging area (dead by now)
+    ln_backward_rows<C, true>(
+        L, lw, sw, [&](int t, int c) { return __ldg(xw + t * C + c); }, [&](int t, int c) { return su[t * LDC + c]; },
         [&](int t, int c, float dz, float zh) {
           dxw[t * C + c] = (resid ? sg[t * LDC + c] : 0.f) + dz;
           const float u = fmaf(zh, __ldg(lw + c), __ldg(lb + c));
           if (FW) su[t * LDC + c] = u; else uw[t * C + c] = u;      // du at (t, c) was consumed by this thread
         });
     __syncthreads();
-    if (a.d_ln_w)
-      for (int i = tid; i < C; i += RL_NT) {
-        atomicAdd(a.d_ln_w + i, s_gb[i]);
-        atomicAdd(a.d_ln_b + i, s_gb[C + i]);
-      }
+    ln_backward_finish<C>(sw, a.d_ln_w, a.d_ln_b);
+    if (FW) __syncthreads();                                        // sw is the weight-gradient scratch next
   } else {
     for (int i = tid; i < L * C; i += RL_NT) {
       const int t = i / C, c = i % C;
@@ -245,9 +247,17 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
     }
     __syncthreads();
   }
-  if (FW) {   // dW2 = g^T g2, dW1 = dh^T u   (u now sits in su)
-    cta_wgrad_mma<C, HC, L>(sg, LDC, sg2, LDH, a.d_w2, a.d_b2, 0);
-    cta_wgrad_mma<HC, C, L>(sd, LDH, su, LDC, a.d_w1, a.d_b1, ((C + 15) / 16) * (HC / 8));
+  if constexpr (FW) {   // dW2 = g^T g2, dW1 = dh^T u   (u now sits in su); both through the one scratch region in sw
+    using W2 = CtaWgrad<C, HC, L>;
+    using W1 = CtaWgrad<HC, C, L>;
+    static_assert(W2::SCRATCH <= ffn_bwd_swf<C>() && W1::SCRATCH <= ffn_bwd_swf<C>(), "ffn_bwd: scratch");
+    W2::partial(sg, LDC, sg2, LDH, sw);
+    __syncthreads();
+    W2::reduce(sw, a.d_w2, a.d_b2);
+    __syncthreads();
+    W1::partial(sd, LDH, su, LDC, sw);
+    __syncthreads();
+    W1::reduce(sw, a.d_w1, a.d_b1);
   }
 }
 

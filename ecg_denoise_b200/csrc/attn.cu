@@ -186,7 +186,6 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   float* sLse = sD + LC / 4;
   float* sw = sLse + LC / 4;
   float* stab = sw + attn_bwd_swf<C>();
-  float* stabg = stab + 128;
   const int tid = threadIdx.x;
   RL_TS(attn, 0);
   const size_t woff = (size_t)blockIdx.x * LC;
@@ -217,7 +216,6 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   copy_rows_g2s(sdq, LDC, gw, L, C);
   cp_async_wait<0>();                                        // saved tensors (and the first weight chunk) have landed
   if (tid < 128) {
-    stabg[tid] = 0.f;
     stab[tid] = (W > 0 && tid < (2 * W - 1) * H) ? __ldg(a.table + tid) * RL_LOG2E : 0.f;
   }
   __syncthreads();
@@ -276,9 +274,17 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   for (int i = tid; i < LP; i += RL_NT) sdq[i] = 0.f;
   __syncthreads();
   RL_TS(attn, 5);
-  attn_core_bwd_single<C, L>(sq, sk, sv, sdo, sD, sLse, sdq, sdk, sdv, stab, stabg, a.d_table != nullptr, W, c0,
-                             1.0f / do_scale);
+  float* sds_c = (a.d_table != nullptr && W > 0) ? su : nullptr;      // su is free until step 6 (H * W * W <= LP floats)
+  attn_core_bwd_single<C, L>(sq, sk, sv, sdo, sD, sLse, sdq, sdk, sdv, stab, sds_c, W, c0, 1.0f / do_scale);
   __syncthreads();
+  if (sds_c != nullptr)           // d_table[i - j + W - 1][h] += sum over the diagonal of the central block of dS
+    for (int idx = tid; idx < (2 * W - 1) * H; idx += RL_NT) {
+      const int rel = idx / H - (W - 1), h = idx % H;
+      const int jlo = (rel < 0) ? -rel : 0, jhi = (rel > 0) ? W - rel : W;
+      float s = 0.f;
+      for (int j = jlo; j < jhi; ++j) s += sds_c[(h * W + j + rel) * W + j];
+      atomicAdd(a.d_table + idx, s);
+    }
   RL_TS(attn, 6);
 
   // 5. dqkv scratch [t][dq | dk | dv] for the weight-gradient GEMMs
@@ -344,8 +350,6 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
     WG::reduce(sv, a.d_wkv, a.d_bkv);
     WG::reduce(sdo, a.d_wkv ? a.d_wkv + C * C : nullptr, a.d_bkv ? a.d_bkv + C : nullptr);
   }
-  if (a.d_table && W > 0)
-    for (int i = tid; i < (2 * W - 1) * H; i += RL_NT) atomicAdd(a.d_table + i, stabg[i]);
   RL_TS(attn, 10);
 }
 

@@ -205,11 +205,15 @@ __device__ __forceinline__ uint32_t col_pair(const uint32_t* base, int ld, int r
 
 // QP (pre-scaled by 0.5 log2e), KP, VP, DP (pre-scaled by do_scale): row-form arrays; sD pre-scaled by do_scale;
 // sdq: fp32, ZEROED, receives 0.5 dS k (plain read-modify-write, see above); sdk, sdv: fp32 outputs.
+// sds_c (may be NULL): [H][W][W] fp32, receives dS of the central block for the gradient of the R-wave table -- plain
+// stores; the diagonals are summed after the core (attn.cu).  (Round 2 added every element to its table entry with a
+// shared-memory atomic: fp32 shared atomics are compare-and-swap loops, up to 8 lanes of a warp hit the same diagonal,
+// and the 7 other key-tile warps of the head waited at the step barrier for the warp that owned a central tile.)
 template <int C, int L>
 __device__ __forceinline__ void attn_core_bwd_single(const float* QPf, const float* KPf, const float* VPf,
                                                      const float* DPf, const float* sD, const float* sLse, float* sdq,
-                                                     float* sdk, float* sdv, const float* stab, float* stabg,
-                                                     bool want_tab, int W, int c0, float inv_do_scale) {
+                                                     float* sdk, float* sdv, const float* stab, float* sds_c,
+                                                     int W, int c0, float inv_do_scale) {
   constexpr int H = C / RL_HD, LDC = ld_mk(C), NW = RL_NT / 32;
   constexpr int JT = L / 16, NITEM = H * JT;
   static_assert(NITEM % NW == 0 && (JT >= NW ? JT % NW == 0 : NW % JT == 0), "bwd core: items must tile the warps");
@@ -268,12 +272,12 @@ __device__ __forceinline__ void attn_core_bwd_single(const float* QPf, const flo
         for (int e = 0; e < 4; ++e) p[e] = fast_ex2(s[e]);
         mul_f32x2(p[0], p[1], dp[0], dp[1], ds[0], ds[1]);
         mul_f32x2(p[2], p[3], dp[2], dp[3], ds[2], ds[3]);
-        if (cen && want_tab) {
+        if (cen && sds_c != nullptr) {     // dS of the central W x W block: every (h, i, j) has exactly one writer
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int i = ib + 2 * t + (e & 1), j = j0 + g + 8 * (e >> 1);
             if ((unsigned)(i - c0) < (unsigned)W && (unsigned)(j - c0) < (unsigned)W)
-              atomicAdd(&stabg[(i - j + W - 1) * H + h], ds[e] * inv_do_scale);
+              sds_c[(h * W + (i - c0)) * W + (j - c0)] = ds[e] * inv_do_scale;
           }
         }
         // accumulator fragments -> A fragments of the query contraction (rows = keys, k = the queries of this half)

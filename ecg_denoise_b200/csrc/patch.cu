@@ -74,7 +74,6 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_bwd_kernel(const rl_patc
   prefetch_l2_block(a.x + (size_t)blockIdx.x * a.L * a.C, rows * CN * 4);   // nor does the saved layer input
   pdl_wait();      // programmatic dependent launch: the previous kernel on the stream has completed
   pdl_trigger();   // let the next kernel get scheduled while this one runs
-  float* s_gb = sw + patch_swf<CN>();
   const int tid = threadIdx.x;
   const size_t woff = (size_t)blockIdx.x * L * C;
   const float* gw = a.g + woff;
@@ -89,7 +88,6 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_bwd_kernel(const rl_patc
     }
     sg[(i / CN) * LDA + (i % CN)] = v;
   }
-  for (int i = tid; i < 2 * CN; i += RL_NT) s_gb[i] = 0.f;
   __syncthreads();
   {
     MmaTile<rows, CN> acc;
@@ -99,16 +97,16 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_bwd_kernel(const rl_patc
   }
   __syncthreads();
   float* dxw = a.dx + woff;
-  ln_backward_rows<CN>(
-      rows, a.ln_w, s_gb, [&](int r, int c) { return __ldg(xw + src_index(mode, L, C, CN, r, c)); },
+  // per-warp partial rows of the LayerNorm weight / bias gradients (16 x 2CN floats): the GEMM operand tile is dead
+  // (2048+ floats), at CN = 128 the weight staging area (8704 floats)
+  float* s_part = (CN <= 64) ? sg : sw;
+  static_assert(CN <= 64 || 32 * CN <= patch_swf<CN>(), "patch_bwd: partial rows");
+  ln_backward_rows<CN, true>(
+      rows, a.ln_w, s_part, [&](int r, int c) { return __ldg(xw + src_index(mode, L, C, CN, r, c)); },
       [&](int r, int c) { return su[r * LDA + c]; },
       [&](int r, int c, float dz, float) { dxw[src_index(mode, L, C, CN, r, c)] = dz; });
   __syncthreads();
-  if (a.d_ln_w)
-    for (int i = tid; i < CN; i += RL_NT) {
-      atomicAdd(a.d_ln_w + i, s_gb[i]);
-      atomicAdd(a.d_ln_b + i, s_gb[CN + i]);
-    }
+  ln_backward_finish<CN>(s_part, a.d_ln_w, a.d_ln_b);
 }
 
 template <int CN>

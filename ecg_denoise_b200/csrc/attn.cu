@@ -73,9 +73,13 @@ __device__ __forceinline__ void attn_fwd_body(const rl_attn_fwd_args& a, float* 
     const float* pe = a.pe;
     const float* lw = a.ln_w;
     const float* lb = a.ln_b;
-    ln_forward_rows<C>(
-        M, [&](int t, int c) { return fmaf(__ldg(xw + t * C + c), sc, __ldg(pe + (t % L) * C + c)); },
-        [&](int t, int c, float zh) { su[t * LDC + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c)); });
+    ln_forward_rows4<C>(
+        M,
+        [&](int t, int c) {
+          const float4 x4 = ldg4(xw + t * C + c), p4 = ldg4(pe + (t % L) * C + c);
+          return make_float4(fmaf(x4.x, sc, p4.x), fmaf(x4.y, sc, p4.y), fmaf(x4.z, sc, p4.z), fmaf(x4.w, sc, p4.w));
+        },
+        [&](int t, int c, float4 zh) { *reinterpret_cast<float4*>(su + t * LDC + c) = fma4(zh, ldg4(lw + c), ldg4(lb + c)); });
   } else {
     copy_rows_g2s(su, LDC, xw, M, C);
   }
@@ -320,13 +324,20 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
     const float* lw = a.ln_w;
     const float* lb = a.ln_b;
     // per-warp partial rows of the LayerNorm weight / bias gradients go to sq..sk (16 x 2C floats; q, k are dead)
-    ln_backward_rows<C, true>(
-        L, lw, sq, [&](int t, int c) { return fmaf(__ldg(xw + t * C + c), sc, __ldg(pe + t * C + c)); },
-        [&](int t, int c) { return su[t * LDC + c]; },
-        [&](int t, int c, float dz, float zh) {
-          dxw[t * C + c] = (resid ? __ldg(gw + t * C + c) : 0.f) + sc * dz;
-          const float u = fmaf(zh, __ldg(lw + c), __ldg(lb + c));
-          if (FW) su[t * LDC + c] = u; else uw[t * C + c] = u;      // du at (t, c) was consumed by this thread
+    ln_backward_rows4<C, true>(
+        L, lw, sq,
+        [&](int t, int c) {
+          const float4 x4 = ldg4(xw + t * C + c), p4 = ldg4(pe + t * C + c);
+          return make_float4(fmaf(x4.x, sc, p4.x), fmaf(x4.y, sc, p4.y), fmaf(x4.z, sc, p4.z), fmaf(x4.w, sc, p4.w));
+        },
+        [&](int t, int c) { return *reinterpret_cast<const float4*>(su + t * LDC + c); },
+        [&](int t, int c, float4 dz, float4 zh) {
+          const float4 g4 = resid ? ldg4(gw + t * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(dxw + t * C + c) =
+              make_float4(fmaf(sc, dz.x, g4.x), fmaf(sc, dz.y, g4.y), fmaf(sc, dz.z, g4.z), fmaf(sc, dz.w, g4.w));
+          const float4 u = fma4(zh, ldg4(lw + c), ldg4(lb + c));
+          // du at (t, c..c+3) was consumed by this thread
+          *reinterpret_cast<float4*>(FW ? su + t * LDC + c : uw + t * C + c) = u;
         });
     __syncthreads();
     ln_backward_finish<C>(sq, a.d_ln_w, a.d_ln_b);
@@ -473,6 +484,9 @@ extern "C" int ralenet_block_fwd(const rl_attn_fwd_args* a, const rl_ffn_fwd_arg
   RL_REQUIRE(!a->q || (a->k && a->v && a->o && a->lse), RL_ERR_NULL, "block_fwd: partial save set");
   RL_REQUIRE(f->y && f->w1 && f->w2 && f->ln_w && f->ln_b, RL_ERR_NULL, "block_fwd: NULL feed-forward tensor");
   RL_REQUIRE(f->le_mode == RL_LE_NONE || f->lew, RL_ERR_NULL, "block_fwd: local-enhancement weights missing");
+  RL_REQUIRE(rl_al16(a->x, a->y, a->pe, a->ln_w, a->ln_b, a->wq, a->wkv, a->wp, a->q, a->k, a->v, a->o, f->y, f->w1, f->w2,
+                     f->ln_w, f->ln_b, f->h, f->extra),
+             RL_ERR_SHAPE, "block_fwd: tensors must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   switch (a->C) {
     case 8: return launch_block_fwd<8>(a, f, st);
@@ -489,6 +503,8 @@ extern "C" int ralenet_attn_fwd(const rl_attn_fwd_args* a, void* stream) {
   RL_REQUIRE(!(a->flags & RL_F_PRENORM) || (a->pe && a->ln_w && a->ln_b), RL_ERR_NULL, "attn_fwd: prenorm needs pe/ln");
   RL_REQUIRE(a->W == 0 || a->table, RL_ERR_NULL, "attn_fwd: W>0 needs table");
   RL_REQUIRE(!a->q || (a->k && a->v && a->o && a->lse), RL_ERR_NULL, "attn_fwd: partial save set");
+  RL_REQUIRE(rl_al16(a->x, a->y, a->pe, a->ln_w, a->ln_b, a->wq, a->wkv, a->wp, a->q, a->k, a->v, a->o), RL_ERR_SHAPE,
+             "attn_fwd: tensors must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   switch (a->C) {
     case 8: return launch_fwd<8>(a, st);
@@ -510,6 +526,9 @@ int rl_attn_bwd_main(const rl_attn_bwd_args* a, cudaStream_t st) {
   RL_REQUIRE(!(a->flags & RL_F_PRENORM) || (a->pe && a->ln_w && a->ln_b), RL_ERR_NULL, "attn_bwd: prenorm needs pe/ln");
   RL_REQUIRE(a->W == 0 || a->table, RL_ERR_NULL, "attn_bwd: W>0 needs table");
   RL_REQUIRE(!a->d_ln_w == !a->d_ln_b, RL_ERR_NULL, "attn_bwd: d_ln_w/d_ln_b must be both set or both NULL");
+  RL_REQUIRE(rl_al16(a->g, a->x, a->pe, a->ln_w, a->ln_b, a->wq, a->wkv, a->wp, a->q, a->k, a->v, a->o, a->lse, a->dx,
+                     a->dqkv, a->u),
+             RL_ERR_SHAPE, "attn_bwd: tensors must be 16-byte aligned");
   switch (a->C) {
     case 8: return launch_bwd<8>(a, st);
     case 16: return launch_bwd<16>(a, st);

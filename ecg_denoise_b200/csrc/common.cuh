@@ -176,6 +176,11 @@ __device__ __forceinline__ void gelu_both2(float x0, float x1, float& g0, float&
   pk_fma(w0, w1, 0.3989422804014327f, 0.3989422804014327f, c0, c1, d0, d1);
 }
 
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
+  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -255,90 +260,87 @@ __device__ __forceinline__ void copy_s2g(float* __restrict__ dst, const float* s
 // LayerNorm over C channels of `rows` tokens (eps 1e-5, biased variance, like nn.LayerNorm).
 // A group of GS = min(C,32) lanes owns one token; each lane holds CPL = C/GS channels.
 // load(t, c) returns the pre-norm value; store(t, c, zhat, rstd_is_unused) receives zhat.
+// (Round 2 gave every lane ONE channel at C <= 32: 16 lanes per token at C = 16, four trips over the 128 tokens with
+// four 4-step shuffle reductions each.  Four consecutive channels per lane make it one trip with 2-step reductions:
+// a quarter of the shuffles, rsqrt and loop overhead -- the LayerNorm phases were 6 - 10 % of the narrow kernels.)
 template <int C>
 struct LnGeom {
-  static constexpr int GS = (C < 32) ? C : 32;
-  static constexpr int CPL = C / GS;
+  static_assert(C % 4 == 0 && C / 4 <= 32, "LnGeom: 8 <= C <= 128, C % 4 == 0");
+  static constexpr int CPL = 4;                       // consecutive channels per lane
+  static constexpr int GS = C / CPL;                  // lanes per token
   static constexpr int TPW = 32 / GS;                 // tokens per warp per iteration
-  static constexpr int TPI = TPW * (RL_NT / 32);      // tokens per CTA iteration
+  static constexpr int TPI = TPW * (RL_NT / 32);      // tokens per CTA iteration (TPI * C = 2048: one trip per window)
 };
 
-template <int C, class Load, class Store>
-__device__ __forceinline__ void ln_forward_rows(int rows, Load load, Store store) {
+// float4 form: load4(t, c) returns the pre-norm values of channels c..c+3 (c % 4 == 0) of token t, store4(t, c, zhat4)
+// receives their normalised values -- one 16-byte access per lane where the caller's arrays allow it
+template <int C, class Load4, class Store4>
+__device__ __forceinline__ void ln_forward_rows4(int rows, Load4 load4, Store4 store4) {
   using G = LnGeom<C>;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gl = lane % G::GS, gi = lane / G::GS;
-  // unrolled (rows is a compile-time constant at the call sites: 1 - 8 trips) so that the global loads of every trip
-  // are in flight together instead of one L2 round trip per trip
+  // unrolled (rows is a compile-time constant at the call sites) so that the global loads of every trip are in flight
+  // together instead of one L2 round trip per trip
 #pragma unroll
   for (int t0 = 0; t0 < rows; t0 += G::TPI) {
     const int t = t0 + warp * G::TPW + gi;
     const bool ok = t < rows;
-    float z[G::CPL];
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < G::CPL; ++i) {
-      z[i] = ok ? load(t, gl + i * G::GS) : 0.f;
-      s += z[i];
-    }
-    const float mu = group_sum<G::GS>(s) * (1.0f / C);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < G::CPL; ++i) {
-      z[i] -= mu;
-      q += z[i] * z[i];
-    }
-    const float rstd = rsqrtf(group_sum<G::GS>(q) * (1.0f / C) + RL_LN_EPS);
-    if (ok) {
-#pragma unroll
-      for (int i = 0; i < G::CPL; ++i) store(t, gl + i * G::GS, z[i] * rstd);
-    }
+    float4 z = ok ? load4(t, 4 * gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float mu = group_sum<G::GS>((z.x + z.y) + (z.z + z.w)) * (1.0f / C);
+    z.x -= mu; z.y -= mu; z.z -= mu; z.w -= mu;
+    const float rstd = rsqrtf(group_sum<G::GS>((z.x * z.x + z.y * z.y) + (z.z * z.z + z.w * z.w)) * (1.0f / C) + RL_LN_EPS);
+    if (ok) store4(t, 4 * gl, make_float4(z.x * rstd, z.y * rstd, z.z * rstd, z.w * rstd));
   }
+}
+// element form: load(t, c) / store(t, c, zhat)
+template <int C, class Load, class Store>
+__device__ __forceinline__ void ln_forward_rows(int rows, Load load, Store store) {
+  ln_forward_rows4<C>(
+      rows, [&](int t, int c) { return make_float4(load(t, c), load(t, c + 1), load(t, c + 2), load(t, c + 3)); },
+      [&](int t, int c, float4 zh) {
+        store(t, c, zh.x); store(t, c + 1, zh.y); store(t, c + 2, zh.z); store(t, c + 3, zh.w);
+      });
 }
 
 // LayerNorm backward for `rows` tokens.
-//   loadz(t,c): pre-norm input;  loaddu(t,c): gradient w.r.t. LN output;  gamma: [C]
-//   emit(t, c, dz, zhat): receives the gradient w.r.t. the pre-norm input and zhat
+//   loadz4(t,c): pre-norm input of channels c..c+3;  loaddu4(t,c): gradient w.r.t. the LN output;  gamma: [C]
+//   emit4(t, c, dz4, zhat4): receives the gradient w.r.t. the pre-norm input and zhat
 //   dgam/dbet partial sums are accumulated into s_gb[0:C] / s_gb[C:2C] (shared, pre-zeroed) with atomics.
 //   WP = true: s_gb is [RL_NT/32][2C], one row of partial sums per WARP written with plain stores (no pre-zeroing, no
 //   shared-memory atomics: those are compare-and-swap loops for fp32 and 16 warps x TPW token groups contend for every
 //   word -- 8 % of the samples of the narrow backward kernels, ncu r2_v32); ln_backward_finish() adds the rows up.
-template <int C, bool WP = false, class LoadZ, class LoadDu, class Emit>
-__device__ __forceinline__ void ln_backward_rows(int rows, const float* __restrict__ gamma, float* s_gb, LoadZ loadz,
-                                                 LoadDu loaddu, Emit emit) {
+template <int C, bool WP = false, class LoadZ4, class LoadDu4, class Emit4>
+__device__ __forceinline__ void ln_backward_rows4(int rows, const float* __restrict__ gamma, float* s_gb, LoadZ4 loadz4,
+                                                  LoadDu4 loaddu4, Emit4 emit4) {
   using G = LnGeom<C>;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gl = lane % G::GS, gi = lane / G::GS;
-  float gam[G::CPL], ag[G::CPL], ab[G::CPL];
-#pragma unroll
-  for (int i = 0; i < G::CPL; ++i) {
-    gam[i] = __ldg(gamma + gl + i * G::GS);
-    ag[i] = 0.f;
-    ab[i] = 0.f;
+  float gam[4], ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+  {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + gl);
+    gam[0] = g4.x; gam[1] = g4.y; gam[2] = g4.z; gam[3] = g4.w;
   }
 #pragma unroll
   for (int t0 = 0; t0 < rows; t0 += G::TPI) {
     const int t = t0 + warp * G::TPW + gi;
     const bool ok = t < rows;
-    float z[G::CPL], du[G::CPL];
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < G::CPL; ++i) {
-      z[i] = ok ? loadz(t, gl + i * G::GS) : 0.f;
-      du[i] = ok ? loaddu(t, gl + i * G::GS) : 0.f;
-      s += z[i];
+    float z[4] = {0.f, 0.f, 0.f, 0.f}, du[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ok) {
+      const float4 z4 = loadz4(t, 4 * gl), d4 = loaddu4(t, 4 * gl);
+      z[0] = z4.x; z[1] = z4.y; z[2] = z4.z; z[3] = z4.w;
+      du[0] = d4.x; du[1] = d4.y; du[2] = d4.z; du[3] = d4.w;
     }
-    const float mu = group_sum<G::GS>(s) * (1.0f / C);
+    const float mu = group_sum<G::GS>((z[0] + z[1]) + (z[2] + z[3])) * (1.0f / C);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < G::CPL; ++i) {
+    for (int i = 0; i < 4; ++i) {
       z[i] -= mu;
       q += z[i] * z[i];
     }
     const float rstd = rsqrtf(group_sum<G::GS>(q) * (1.0f / C) + RL_LN_EPS);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < G::CPL; ++i) {
+    for (int i = 0; i < 4; ++i) {
       z[i] *= rstd;                       // zhat
       ag[i] += du[i] * z[i];
       ab[i] += du[i];
@@ -348,31 +350,44 @@ __device__ __forceinline__ void ln_backward_rows(int rows, const float* __restri
     }
     s1 = group_sum<G::GS>(s1) * (1.0f / C);
     s2 = group_sum<G::GS>(s2) * (1.0f / C);
-    if (ok) {
-#pragma unroll
-      for (int i = 0; i < G::CPL; ++i) emit(t, gl + i * G::GS, rstd * (du[i] - s1 - z[i] * s2), z[i]);
-    }
+    if (ok)
+      emit4(t, 4 * gl,
+            make_float4(rstd * (du[0] - s1 - z[0] * s2), rstd * (du[1] - s1 - z[1] * s2), rstd * (du[2] - s1 - z[2] * s2),
+                        rstd * (du[3] - s1 - z[3] * s2)),
+            make_float4(z[0], z[1], z[2], z[3]));
   }
   if (WP) {
 #pragma unroll
-    for (int i = 0; i < G::CPL; ++i) {
+    for (int i = 0; i < 4; ++i) {
 #pragma unroll
       for (int o = G::GS; o < 32; o <<= 1) {            // the TPW token groups of this warp hold the same channels
         ag[i] += __shfl_xor_sync(0xffffffffu, ag[i], o);
         ab[i] += __shfl_xor_sync(0xffffffffu, ab[i], o);
       }
-      if (gi == 0) {
-        s_gb[warp * 2 * C + gl + i * G::GS] = ag[i];
-        s_gb[warp * 2 * C + C + gl + i * G::GS] = ab[i];
-      }
+    }
+    if (gi == 0) {
+      *reinterpret_cast<float4*>(s_gb + warp * 2 * C + 4 * gl) = make_float4(ag[0], ag[1], ag[2], ag[3]);
+      *reinterpret_cast<float4*>(s_gb + warp * 2 * C + C + 4 * gl) = make_float4(ab[0], ab[1], ab[2], ab[3]);
     }
   } else if (s_gb != nullptr) {
 #pragma unroll
-    for (int i = 0; i < G::CPL; ++i) {
-      atomicAdd(&s_gb[gl + i * G::GS], ag[i]);
-      atomicAdd(&s_gb[C + gl + i * G::GS], ab[i]);
+    for (int i = 0; i < 4; ++i) {
+      atomicAdd(&s_gb[4 * gl + i], ag[i]);
+      atomicAdd(&s_gb[C + 4 * gl + i], ab[i]);
     }
   }
+}
+// element form: loadz(t,c), loaddu(t,c), emit(t, c, dz, zhat)
+template <int C, bool WP = false, class LoadZ, class LoadDu, class Emit>
+__device__ __forceinline__ void ln_backward_rows(int rows, const float* __restrict__ gamma, float* s_gb, LoadZ loadz,
+                                                 LoadDu loaddu, Emit emit) {
+  ln_backward_rows4<C, WP>(
+      rows, gamma, s_gb,
+      [&](int t, int c) { return make_float4(loadz(t, c), loadz(t, c + 1), loadz(t, c + 2), loadz(t, c + 3)); },
+      [&](int t, int c) { return make_float4(loaddu(t, c), loaddu(t, c + 1), loaddu(t, c + 2), loaddu(t, c + 3)); },
+      [&](int t, int c, float4 dz, float4 zh) {
+        emit(t, c, dz.x, zh.x); emit(t, c + 1, dz.y, zh.y); emit(t, c + 2, dz.z, zh.z); emit(t, c + 3, dz.w, zh.w);
+      });
 }
 // after a CTA barrier behind ln_backward_rows<C, true>: d_ln_w / d_ln_b += the per-warp partial rows
 template <int C>
@@ -891,6 +906,11 @@ struct CtaWgrad {
     }
   }
 };
+
+// true when every pointer is NULL or 16-byte aligned (the kernels use 16-byte accesses on activations, weights,
+// LayerNorm vectors and the positional tile)
+template <class... P>
+inline bool rl_al16(P... p) { return (((uintptr_t)p | ...) & 15) == 0; }
 
 // generic weight-gradient GEMM launcher (wgrad.cu):
 //   dW[n*K + k] += sum_m dY[m*ldy + n] * X[m*ldx + k]      n < N, k < K, m < M

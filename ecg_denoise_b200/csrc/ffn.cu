@@ -229,12 +229,17 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
     const float* lw = a.ln_w;
     const float* lb = a.ln_b;
     // per-warp partial rows of the LayerNorm weight / bias gradients go to the weight staging area (dead by now)
-    ln_backward_rows<C, true>(
-        L, lw, sw, [&](int t, int c) { return __ldg(xw + t * C + c); }, [&](int t, int c) { return su[t * LDC + c]; },
-        [&](int t, int c, float dz, float zh) {
-          dxw[t * C + c] = (resid ? sg[t * LDC + c] : 0.f) + dz;
-          const float u = fmaf(zh, __ldg(lw + c), __ldg(lb + c));
-          if (FW) su[t * LDC + c] = u; else uw[t * C + c] = u;      // du at (t, c) was consumed by this thread
+    ln_backward_rows4<C, true>(
+        L, lw, sw, [&](int t, int c) { return ldg4(xw + t * C + c); },
+        [&](int t, int c) { return *reinterpret_cast<const float4*>(su + t * LDC + c); },
+        [&](int t, int c, float4 dz, float4 zh) {
+          if (resid) {
+            const float4 g4 = *reinterpret_cast<const float4*>(sg + t * LDC + c);
+            dz.x += g4.x; dz.y += g4.y; dz.z += g4.z; dz.w += g4.w;
+          }
+          *reinterpret_cast<float4*>(dxw + t * C + c) = dz;
+          // du at (t, c..c+3) was consumed by this thread
+          *reinterpret_cast<float4*>(FW ? su + t * LDC + c : uw + t * C + c) = fma4(zh, ldg4(lw + c), ldg4(lb + c));
         });
     __syncthreads();
     ln_backward_finish<C>(sw, a.d_ln_w, a.d_ln_b);
@@ -305,6 +310,8 @@ extern "C" int ralenet_ffn_fwd(const rl_ffn_fwd_args* a, void* stream) {
   RL_REQUIRE(a->x && a->y && a->w1 && a->w2, RL_ERR_NULL, "ffn_fwd: NULL tensor");
   RL_REQUIRE(!(a->flags & RL_F_PRENORM) || (a->ln_w && a->ln_b), RL_ERR_NULL, "ffn_fwd: prenorm needs ln");
   RL_REQUIRE(a->le_mode == RL_LE_NONE || a->lew, RL_ERR_NULL, "ffn_fwd: le_mode needs lew");
+  RL_REQUIRE(rl_al16(a->x, a->y, a->w1, a->w2, a->ln_w, a->ln_b, a->h, a->extra), RL_ERR_SHAPE,
+             "ffn_fwd: tensors must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   {
     int rc = rl_ffn_fwd_umma(a, st);
@@ -330,6 +337,8 @@ int rl_ffn_bwd_main(const rl_ffn_bwd_args* a, cudaStream_t st) {
   RL_REQUIRE(!(a->flags & RL_F_PRENORM) || (a->ln_w && a->ln_b), RL_ERR_NULL, "ffn_bwd: prenorm needs ln");
   RL_REQUIRE(a->le_mode == RL_LE_NONE || a->lew, RL_ERR_NULL, "ffn_bwd: le_mode needs lew");
   RL_REQUIRE(!a->d_ln_w == !a->d_ln_b, RL_ERR_NULL, "ffn_bwd: d_ln_w/d_ln_b must be both set or both NULL");
+  RL_REQUIRE(rl_al16(a->g, a->x, a->w1, a->w2, a->ln_w, a->ln_b, a->h, a->dx, a->dh, a->g2, a->u), RL_ERR_SHAPE,
+             "ffn_bwd: tensors must be 16-byte aligned");
   int rc = rl_ffn_bwd_umma(a, st);
   if (rc < 0) return rc;
   if (rc == 1) rc = rl_ffn_bwd_cluster(a, st);

@@ -38,9 +38,13 @@ __device__ __forceinline__ void ffn_fwd_body(const rl_ffn_fwd_args& a, float* sm
   if (a.flags & RL_F_PRENORM) {
     const float* lw = a.ln_w;
     const float* lb = a.ln_b;
-    ln_forward_rows<C>(
-        L, [&](int t, int c) { return CHAIN ? __ldcg(xw + t * C + c) : __ldg(xw + t * C + c); },
-        [&](int t, int c, float zh) { su[t * LDC + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c)); });
+    ln_forward_rows4<C>(
+        L,
+        [&](int t, int c) {
+          const float4* p4 = reinterpret_cast<const float4*>(xw + t * C + c);
+          return CHAIN ? __ldcg(p4) : __ldg(p4);
+        },
+        [&](int t, int c, float4 zh) { *reinterpret_cast<float4*>(su + t * LDC + c) = fma4(zh, ldg4(lw + c), ldg4(lb + c)); });
   } else {
     copy_rows_g2s(su, LDC, xw, L, C);
   }

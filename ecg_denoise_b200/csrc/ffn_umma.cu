@@ -452,7 +452,6 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_umma_kernel(const rl_f
     umma::fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc<TMEM_COLS>(tmem_slot);
-  for (int i = tid; i < 2 * C; i += RL_NT) s_gb[i] = 0.f;
 
   // 1. g tile -> A (K-major, KT = C) with remainder
   {
@@ -662,33 +661,43 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_umma_kernel(const rl_f
     const float* xr = a.x + (tok0 + row0) * C;
     const float* gr = gw + (size_t)row0 * C;
     const bool resid = a.flags & RL_F_RESIDUAL;
-    auto du_at = [&](int t, int c) {
+    auto du_at4 = [&](int t, int c) {          // four channels of the reduced partial tiles (16-byte DSMEM loads)
       const int off = (row0 + t) * LDP + c;
-      float s = part[0][off];
+      float4 s = *reinterpret_cast<const float4*>(part[0] + off);
 #pragma unroll
-      for (int q = 1; q < NSL; ++q) s += part[q][off];
+      for (int q = 1; q < NSL; ++q) {
+        const float4 p = *reinterpret_cast<const float4*>(part[q] + off);
+        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+      }
       return s;
     };
     if (a.flags & RL_F_PRENORM) {
       const float* lw = a.ln_w;
       const float* lb = a.ln_b;
-      ln_backward_rows<C>(
-          rows_here, lw, s_gb, [&](int t, int c) { return __ldg(xr + t * C + c); }, du_at,
-          [&](int t, int c, float dz, float zh) {
-            dxw[t * C + c] = (resid ? __ldg(gr + t * C + c) : 0.f) + dz;
-            uw[t * C + c] = fmaf(zh, __ldg(lw + c), __ldg(lb + c));
+      // per-warp partial rows of the LayerNorm weight / bias gradients: the weight ring (dead by now), 16 x 2C floats
+      static_assert(32 * C <= 4 * BwdSmem<C>::B_FLOATS, "ffn_bwd_umma: partial rows");
+      ln_backward_rows4<C, true>(
+          rows_here, lw, sB, [&](int t, int c) { return ldg4(xr + t * C + c); }, du_at4,
+          [&](int t, int c, float4 dz, float4 zh) {
+            if (resid) {
+              const float4 g4 = ldg4(gr + t * C + c);
+              dz.x += g4.x; dz.y += g4.y; dz.z += g4.z; dz.w += g4.w;
+            }
+            *reinterpret_cast<float4*>(dxw + t * C + c) = dz;
+            *reinterpret_cast<float4*>(uw + t * C + c) = fma4(zh, ldg4(lw + c), ldg4(lb + c));
           });
       __syncthreads();
-      if (a.d_ln_w)
-        for (int i = tid; i < C; i += RL_NT) {
-          atomicAdd(a.d_ln_w + i, s_gb[i]);
-          atomicAdd(a.d_ln_b + i, s_gb[C + i]);
-        }
+      ln_backward_finish<C>(sB, a.d_ln_w, a.d_ln_b);
     } else {
-      for (int i = tid; i < rows_here * C; i += RL_NT) {
-        const int t = i / C, c = i % C;
-        dxw[i] = du_at(t, c) + (resid ? __ldg(gr + i) : 0.f);
-        uw[i] = __ldg(xr + i);
+      for (int i = tid; i < rows_here * C / 4; i += RL_NT) {
+        const int t = (4 * i) / C, c = (4 * i) % C;
+        float4 d = du_at4(t, c);
+        if (resid) {
+          const float4 g4 = ldg4(gr + 4 * i);
+          d.x += g4.x; d.y += g4.y; d.z += g4.z; d.w += g4.w;
+        }
+        *reinterpret_cast<float4*>(dxw + 4 * i) = d;
+        *reinterpret_cast<float4*>(uw + 4 * i) = ldg4(xr + 4 * i);
       }
     }
   }

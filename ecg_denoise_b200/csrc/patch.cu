@@ -42,12 +42,13 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_fwd_kernel(const rl_patc
     const float* lw = a.ln_w;
     const float* lb = a.ln_b;
     float* us = a.u ? a.u + woff : nullptr;
-    ln_forward_rows<CN>(
-        rows, [&](int r, int c) { return __ldg(xw + src_index(mode, L, C, CN, r, c)); },
-        [&](int r, int c, float zh) {
-          const float u = fmaf(zh, __ldg(lw + c), __ldg(lb + c));
-          su[r * LDA + c] = u;
-          if (us) us[r * CN + c] = u;
+    // (four consecutive channels of a re-laid-out row are consecutive in the source in both modes: 16-byte accesses)
+    ln_forward_rows4<CN>(
+        rows, [&](int r, int c) { return ldg4(xw + src_index(mode, L, C, CN, r, c)); },
+        [&](int r, int c, float4 zh) {
+          const float4 u = fma4(zh, ldg4(lw + c), ldg4(lb + c));
+          *reinterpret_cast<float4*>(su + r * LDA + c) = u;
+          if (us) *reinterpret_cast<float4*>(us + r * CN + c) = u;
         });
   }
   __syncthreads();
@@ -101,10 +102,10 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_bwd_kernel(const rl_patc
   // (2048+ floats), at CN = 128 the weight staging area (8704 floats)
   float* s_part = (CN <= 64) ? sg : sw;
   static_assert(CN <= 64 || 32 * CN <= patch_swf<CN>(), "patch_bwd: partial rows");
-  ln_backward_rows<CN, true>(
-      rows, a.ln_w, s_part, [&](int r, int c) { return __ldg(xw + src_index(mode, L, C, CN, r, c)); },
-      [&](int r, int c) { return su[r * LDA + c]; },
-      [&](int r, int c, float dz, float) { dxw[src_index(mode, L, C, CN, r, c)] = dz; });
+  ln_backward_rows4<CN, true>(
+      rows, a.ln_w, s_part, [&](int r, int c) { return ldg4(xw + src_index(mode, L, C, CN, r, c)); },
+      [&](int r, int c) { return *reinterpret_cast<const float4*>(su + r * LDA + c); },
+      [&](int r, int c, float4 dz, float4) { *reinterpret_cast<float4*>(dxw + src_index(mode, L, C, CN, r, c)) = dz; });
   __syncthreads();
   ln_backward_finish<CN>(s_part, a.d_ln_w, a.d_ln_b);
 }
@@ -154,6 +155,8 @@ extern "C" int ralenet_patch_fwd(const rl_patch_fwd_args* a, void* stream) {
   int CN = 0;
   if (int rc = check_shape(a->B, a->L, a->C, a->mode, &CN)) return rc;
   RL_REQUIRE(a->x && a->y && a->w && a->ln_w && a->ln_b, RL_ERR_NULL, "patch_fwd: NULL tensor");
+  RL_REQUIRE(rl_al16(a->x, a->y, a->w, a->ln_w, a->ln_b, a->u, a->skip), RL_ERR_SHAPE,
+             "patch_fwd: tensors must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   switch (CN) {
     case 8: return launch_fwd<8>(a, st);
@@ -174,6 +177,8 @@ int rl_patch_bwd_main(const rl_patch_bwd_args* a, cudaStream_t st) {
   RL_REQUIRE(a->g && a->x && a->w && a->ln_w && a->u && a->dx, RL_ERR_NULL, "patch_bwd: NULL tensor");
   RL_REQUIRE(!a->d_ln_w == !a->d_ln_b, RL_ERR_NULL, "patch_bwd: d_ln_w/d_ln_b must be both set or both NULL");
   RL_REQUIRE(!a->g2 || a->gsum, RL_ERR_NULL, "patch_bwd: g2 needs the gsum scratch");
+  RL_REQUIRE(rl_al16(a->g, a->g2, a->gsum, a->x, a->w, a->ln_w, a->u, a->dx), RL_ERR_SHAPE,
+             "patch_bwd: tensors must be 16-byte aligned");
   switch (CN) {
     case 8: return launch_bwd<8>(a, a->gsum, st);
     case 16: return launch_bwd<16>(a, a->gsum, st);

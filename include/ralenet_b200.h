@@ -8,7 +8,9 @@
  * in ecg_denoise_b200/model/ and binds these symbols with ctypes.
  *
  * Conventions
- *   - plain C: raw device pointers + sizes, no torch types.  All tensors are fp32, contiguous.
+ *   - plain C: raw device pointers + sizes, no torch types.  All tensors are fp32, contiguous and
+ *     16-byte aligned (activations, weights, LayerNorm vectors and positional tiles are accessed 16
+ *     bytes at a time; a misaligned pointer is rejected with RL_ERR_SHAPE).
  *   - activations inside the network are token-major [B][L][C] (the reference's layout after
  *     rearrange 'b c l -> b l c', model/transformer.py:630).  One "window" = one ECG window.
  *   - the library never allocates, frees or synchronises: every buffer (incl. workspaces) is owned

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   float* sw = sLse + LC / 4;
   float* stab = sw + attn_bwd_swf<C>();
   const int tid = threadIdx.x;
+  __shared__ float s_amax[RL_NT / 32];
   RL_TS(attn, 0);
   const size_t woff = (size_t)blockIdx.x * LC;
   {   // The tensors the forward pass saved for this window -- q, k, v, o, lse -- do not depend on the preceding kernel
@@ -231,7 +232,16 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
     acc.init();
     AttnW<C>::DProj::template run<true>(acc, sdq, LDC, sw, a.wp, 1 << 30, nullptr, C);
     AttnW<C>::Dgrad::prefetch(sw, a.wq, C, a.wkv, C);         // lands while the attention core runs
-    acc.epilogue([&](int t, int n, float v) { sdo[t * LDC + n] = v; });
+    // max |do| of the window is taken from the accumulators on their way to shared memory (one barrier and one pass
+    // over the tile less than reading it back)
+    float am = 0.f;
+    acc.epilogue([&](int t, int n, float v) {
+      sdo[t * LDC + n] = v;
+      am = fmaxf(am, fabsf(v));
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+    if ((tid & 31) == 0) s_amax[tid >> 5] = am;
   }
   __syncthreads();
   RL_TS(attn, 3);
@@ -239,14 +249,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   //    hi/lo pairs; gradients are ~1e-6 and would underflow unscaled), then D[h,i] = do_i . o_i (scaled alike)
   float do_scale;
   {
-    __shared__ float s_amax[RL_NT / 32];
-    float am = 0.f;
-    for (int i = tid; i < LC; i += RL_NT) am = fmaxf(am, fabsf(sdo[(i / C) * LDC + (i % C)]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
-    if ((tid & 31) == 0) s_amax[tid >> 5] = am;
-    __syncthreads();
-    am = s_amax[0];
+    float am = s_amax[0];
 #pragma unroll
     for (int w = 1; w < RL_NT / 32; ++w) am = fmaxf(am, s_amax[w]);
     do_scale = (am > 0.f && am < 3e38f) ? exp2f(6.f - ceilf(log2f(am))) : 1.f;

@@ -79,8 +79,13 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
   float* dhw = a.dh + hoff;
   const int mode = a.le_mode;
 
-  // 1. g -> sg; the pieces of g1 = GELU(h) that cross tokens
-  copy_rows_g2s(sg, LDC, gw, L, C);
+  // 1. g -> sg (asynchronously: its round trip passes behind the loads / GELUs of the cross-token pieces below);
+  //    the pieces of g1 = GELU(h) that cross tokens
+  for (int i = tid; i < L * (C / 4); i += RL_NT) {
+    const int r = i / (C / 4), c = (i % (C / 4)) * 4;
+    cp_async16(sg + r * LDC + c, gw + r * C + c);
+  }
+  cp_async_commit();
   float lw0 = 0.f, lw1 = 0.f, lw2 = 0.f;
   if (DW) {
     for (int i = tid; i < L * HC; i += RL_NT) sh[(i / HC) * LDH + (i % HC)] = gelu_f(__ldg(hw + i));
@@ -94,6 +99,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
       sf0[t] = lw0 * p + lw1 * sg10[t] + lw2 * n;
     }
   }
+  cp_async_wait<0>();                                   // g (and the first weight chunk) have landed
   __syncthreads();
   if (DW) {   // g2 = GELU(fir(g1)) for the fc2 weight gradient
     for (int i = tid; i < L * HC; i += RL_NT) {

@@ -220,6 +220,11 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
   // 1. g -> sdq (temp); o sits in sdk (temp)
   copy_rows_g2s(sdq, LDC, gw, L, C);
   cp_async_wait<0>();                                        // saved tensors (and the first weight chunk) have landed
+  for (int i = tid; i < LC / 16; i += RL_NT) {               // the core wants -lse: each thread negates the 16 bytes its
+    float4* p = reinterpret_cast<float4*>(sLse + 4 * i);     // own cp.async wrote (visible to it after the wait above)
+    const float4 v = *p;
+    *p = make_float4(-v.x, -v.y, -v.z, -v.w);
+  }
   if (tid < 128) {
     stab[tid] = (W > 0 && tid < (2 * W - 1) * H) ? __ldg(a.table + tid) * RL_LOG2E : 0.f;
   }
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
     const int i = item % L, h = item / L;
     const float4 d4 = *reinterpret_cast<const float4*>(sdo + i * LDC + 4 * h);
     const float4 o4 = *reinterpret_cast<const float4*>(sdk + i * LDC + 4 * h);
-    sD[item] = do_scale * (d4.x * o4.x + d4.y * o4.y + d4.z * o4.z + d4.w * o4.w);
+    sD[item] = -do_scale * (d4.x * o4.x + d4.y * o4.y + d4.z * o4.z + d4.w * o4.w);     // the core wants -D
   }
   __syncthreads();
 

@@ -200,13 +200,15 @@ __device__ __forceinline__ void to_row_form(float* s, int ld, int rows, float sc
 }
 // one register of a "pairs along rows" operand built from two row-form words: the fp16 of dim-slot `slot`
 // (0-3: hi of dims 0-3, 4-7: lo) of rows r and r+1 (row r in the low half)
-__device__ __forceinline__ uint32_t col_pair(const uint32_t* base, int ld, int r, int slot) {
+// (the byte selector is a per-lane constant: one PRMT with a register selector instead of two predicated ones)
+__device__ __forceinline__ uint32_t col_pair_sel(int slot) { return (slot & 1) ? 0x7632u : 0x5410u; }
+__device__ __forceinline__ uint32_t col_pair(const uint32_t* base, int ld, int r, int slot, uint32_t sel) {
   const int word = (slot >> 2) * 2 + ((slot & 3) >> 1);
-  const uint32_t a = base[r * ld + word], b = base[(r + 1) * ld + word];
-  return (slot & 1) ? __byte_perm(a, b, 0x7632) : __byte_perm(a, b, 0x5410);
+  return __byte_perm(base[r * ld + word], base[(r + 1) * ld + word], sel);
 }
 
-// QP (pre-scaled by 0.5 log2e), KP, VP, DP (pre-scaled by do_scale): row-form arrays; sD pre-scaled by do_scale;
+// QP (pre-scaled by 0.5 log2e), KP, VP, DP (pre-scaled by do_scale): row-form arrays; sD = -do_scale * D and
+// sLse = -lse: both NEGATED by the caller (8 negations per step less in the walk);
 // sdq: fp32, ZEROED, receives 0.5 dS k (plain read-modify-write, see above); sdk, sdv: fp32 outputs.
 // sds_c (may be NULL): [H][W][W] fp32, receives dS of the central block for the gradient of the R-wave table -- plain
 // stores; the diagonals are summed after the core (attn.cu).  (Round 2 added every element to its table entry with a
@@ -226,6 +228,7 @@ __device__ __forceinline__ void attn_core_bwd_single(const float* QPf, const flo
   const uint32_t* VP = reinterpret_cast<const uint32_t*>(VPf);
   const uint32_t* DP = reinterpret_cast<const uint32_t*>(DPf);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const uint32_t psel = col_pair_sel(g);
   const float f_dq = 0.5f * inv_do_scale;                       // dq = 0.5 dS k
   const float f_dk = inv_do_scale / RL_LOG2E;                   // dk = 0.5 dS q, q carried as q * 0.5 log2e
 #pragma unroll 1
@@ -237,8 +240,8 @@ __device__ __forceinline__ void attn_core_bwd_single(const float* QPf, const flo
       ka[0] = KP[o0]; ka[1] = KP[o0 + 8 * LDC]; ka[2] = KP[o0 + 2]; ka[3] = KP[o0 + 8 * LDC + 2];
       va[0] = VP[o0]; va[1] = VP[o0 + 8 * LDC]; va[2] = VP[o0 + 2]; va[3] = VP[o0 + 8 * LDC + 2];
       // k^T for dq^T = k^T dS^T: rows = dim slots (g < 8), k = keys (2t, 2t+1) and (2t+8, 2t+9); rows 8-15 unused
-      kt[0] = col_pair(KP + 4 * h, LDC, j0 + 2 * t, g);
-      kt[2] = col_pair(KP + 4 * h, LDC, j0 + 2 * t + 8, g);
+      kt[0] = col_pair(KP + 4 * h, LDC, j0 + 2 * t, g, psel);
+      kt[2] = col_pair(KP + 4 * h, LDC, j0 + 2 * t + 8, g, psel);
       kt[1] = kt[3] = 0u;
     }
     float ak[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
@@ -256,10 +259,10 @@ __device__ __forceinline__ void attn_core_bwd_single(const float* QPf, const flo
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int ib = i0 + 8 * hf;
-        // the accumulators start at -lse / -D, so the MMAs deliver S^T - lse and dP^T - D directly
+        // the accumulators start at -lse / -D (stored negated), so the MMAs deliver S^T - lse and dP^T - D directly
         const float2 ls = *reinterpret_cast<const float2*>(lsep + ib);
         const float2 Dd = *reinterpret_cast<const float2*>(Dp + ib);
-        float s[4] = {-ls.x, -ls.y, -ls.x, -ls.y}, dp[4] = {-Dd.x, -Dd.y, -Dd.x, -Dd.y};
+        float s[4] = {ls.x, ls.y, ls.x, ls.y}, dp[4] = {Dd.x, Dd.y, Dd.x, Dd.y};
         {
           const uint32_t bq = QP[(ib + g) * LDC + 4 * h + t], bd = DP[(ib + g) * LDC + 4 * h + t];
           const uint32_t b0[2] = {bq, bq}, b1[2] = {bd, bd};
@@ -308,8 +311,10 @@ __device__ __forceinline__ void attn_core_bwd_single(const float* QPf, const flo
       }
       // dv += P^T dO, dk += dS^T q over the 16 queries: B = (query pairs) x (dim slots)
       {
-        const uint32_t bd[2] = {col_pair(DP + 4 * h, LDC, i0 + 2 * t, g), col_pair(DP + 4 * h, LDC, i0 + 2 * t + 8, g)};
-        const uint32_t bq[2] = {col_pair(QP + 4 * h, LDC, i0 + 2 * t, g), col_pair(QP + 4 * h, LDC, i0 + 2 * t + 8, g)};
+        const uint32_t bd[2] = {col_pair(DP + 4 * h, LDC, i0 + 2 * t, g, psel),
+                                col_pair(DP + 4 * h, LDC, i0 + 2 * t + 8, g, psel)};
+        const uint32_t bq[2] = {col_pair(QP + 4 * h, LDC, i0 + 2 * t, g, psel),
+                                col_pair(QP + 4 * h, LDC, i0 + 2 * t + 8, g, psel)};
         mma_f16(av, pah, bd);
         mma_f16(ak, dah, bq);
         mma_f16(av, pal, bd);

@@ -513,9 +513,20 @@ def train12_record(dev, world, rank, steps, warmup):
         f1.record()
         torch.cuda.synchronize()
         fms = f0.elapsed_time(f1)
+        ft.prefetch_host(hx, ht)                   # (warm-up of the pipelined loop: staging pair, copy stream, slots)
+        ft.read_async(ft.step_host(hx, ht))()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(steps):
-            fl = ft.step_host(hx, ht).item()
+        ft.prefetch_host(hx, ht)
+        pend = []
+        for _ in range(steps):                    # same software pipeline as the main e2e loop (see main())
+            pend.append(ft.read_async(ft.step_host(hx, ht)))
+            ft.prefetch_host(hx, ht)
+            if len(pend) > 2:
+                fl = pend.pop(0)()
+        while pend:
+            fl = pend.pop(0)()
+        torch.cuda.synchronize()
         fms_e2e = 1e3 * (time.perf_counter() - t0)
         fused = {"value": B * steps / (fms * 1e-3), "unit": "12-lead windows/s", "ms_per_step": fms / steps,
                  "e2e": {"value": B * steps / (fms_e2e * 1e-3), "unit": "12-lead windows/s",
@@ -764,15 +775,30 @@ def main():
     final_loss = float(loss.item())
 
     # ---- end to end: pinned host batch -> H2D -> step -> D2H loss ---------------------------------------
-    for i in range(3):
-        trainer.step_host(hx[i % NB], ht[i % NB]).item()
+    for i in range(3):                            # warm-up of the same loop (staging buffers, copy stream, pinned slots)
+        trainer.prefetch_host(hx[i % NB], ht[i % NB])
+        trainer.read_async(trainer.step_host(hx[i % NB], ht[i % NB]))()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e2.record()
+    # Software-pipelined loop: the copy of batch i + 1 runs on a copy stream under step i (the one-batch-ahead prefetch
+    # of any pinned-memory input pipeline), and the loss of step i is read on the host after step i + 2 has been
+    # enqueued, so the GPU does not idle on the host round trip.  Every step's inputs are copied from the host and every
+    # step's loss is read by the host inside the timed region.
+    # (two steps of slack: with one, a single host hiccup -- e.g. the driver lock taken by the nvidia-smi clock sampler
+    #  above -- longer than a 2 ms step leaves the GPU idle; measured 50 us/step at 30 steps, tools/exp_e2e_gap.py)
+    LAG = 2
+    trainer.prefetch_host(hx[0], ht[0])
+    pending = []
     for i in range(args.steps):
         l = trainer.step_host(hx[i % NB], ht[i % NB])
-        host_loss = l.item()                      # device -> host read of the step's result, every step
+        pending.append(trainer.read_async(l))     # device -> host read of this step's result, collected LAG steps later
+        trainer.prefetch_host(hx[(i + 1) % NB], ht[(i + 1) % NB])
+        if len(pending) > LAG:
+            host_loss = pending.pop(0)()
+    while pending:
+        host_loss = pending.pop(0)()
     e3.record()
     barrier()
     ms_e2e = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
@@ -907,7 +933,10 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bytes_in,
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                    "loop": "FusedTrainer.step_host from pinned host batches; batch i+1 copied on a copy stream under "
+                            "step i (prefetch_host), the loss of step i read on the host after step i+2 is enqueued "
+                            "(read_async); every copy and every read inside the timed region"},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "clocks": clocks, "final_loss": final_loss, "cuda_graph": args.graph == "on", "exchange": comm_kind,
             "roofline": roofline, "whole_step": whole, "cpu_baseline": cpu_base,

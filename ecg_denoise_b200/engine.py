@@ -346,7 +346,72 @@ class RalenetFn(torch.autograd.Function):
         return dx, None, None
 
 
-class FusedTrainer:
+class _HostPipeline:
+    """Host side of a software-pipelined training loop, shared by FusedTrainer and FineTuneTrainer:
+    prefetch_host() copies the NEXT batch host -> device on a copy stream under the running step, step_host() picks the
+    staged copy up, read_async() brings a step result back without stalling the enqueue of the following steps.
+    The trainer provides _host_static(shape) -> (x, target) static device buffers."""
+    _stage = None                     # staging pair, copy stream, events
+    _staged_key = None
+    _loss_slots = None                # pinned result slots
+
+    def prefetch_host(self, hx: torch.Tensor, ht: torch.Tensor) -> None:
+        """input-pipeline prefetch (what a DataLoader with pin_memory + non_blocking copies does): start the H2D copy of
+        the NEXT batch from (pinned) HOST tensors into a staging pair on a copy stream, so that it runs under the step
+        that is executing; the next step_host() called with the same two tensors takes the staged copy (a device to
+        device copy) instead of copying from the host.  The batch is captured when this is called."""
+        sx, st_ = self._host_static(hx.shape)
+        dev = sx.device
+        if self._stage is None or self._stage[0].shape != sx.shape:
+            self._stage = (torch.empty_like(sx), torch.empty_like(st_))
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._stage_ready, self._stage_free = torch.cuda.Event(), torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream(dev))
+        cs = self._copy_stream
+        cs.wait_event(self._stage_free)               # the previous staged batch has been moved to the static buffers
+        with torch.cuda.stream(cs):
+            self._stage[0].copy_(hx, non_blocking=True)
+            self._stage[1].copy_(ht, non_blocking=True)
+            self._stage_ready.record(cs)
+        self._staged_key = (hx.data_ptr(), ht.data_ptr(), tuple(hx.shape))
+
+    def _load_host_batch(self, hx: torch.Tensor, ht: torch.Tensor):
+        """static device buffers <- the copy prefetch_host() staged for these tensors, else the host tensors."""
+        sx, st_ = self._host_static(hx.shape)
+        if self._staged_key == (hx.data_ptr(), ht.data_ptr(), tuple(hx.shape)):
+            main = torch.cuda.current_stream(sx.device)
+            main.wait_event(self._stage_ready)
+            sx.copy_(self._stage[0], non_blocking=True)
+            st_.copy_(self._stage[1], non_blocking=True)
+            self._stage_free.record(main)
+            self._staged_key = None
+        else:
+            sx.copy_(hx, non_blocking=True)
+            st_.copy_(ht, non_blocking=True)
+        return sx, st_
+
+    def read_async(self, dev_scalar: torch.Tensor):
+        """start the device -> host copy of a step result (e.g. the loss tensor step_host() returned -- with use_graph
+        that is a static buffer the next replay overwrites) into a pinned slot and return a callable that waits for
+        it and gives the Python float.  Lets a loop enqueue steps i + 1, i + 2 before it reads the loss of step i, so
+        the GPU never idles on the host round trip (at most 3 results may be outstanding)."""
+        if self._loss_slots is None:
+            self._loss_slots = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._loss_events = [torch.cuda.Event() for _ in range(4)]
+            self._loss_i = 0
+        k = self._loss_i
+        self._loss_i = (k + 1) % 4
+        slot, ev = self._loss_slots[k], self._loss_events[k]
+        slot.copy_(dev_scalar.reshape(1), non_blocking=True)
+        ev.record(torch.cuda.current_stream(dev_scalar.device))
+
+        def result() -> float:
+            ev.synchronize()
+            return float(slot[0])
+        return result
+
+
+class FusedTrainer(_HostPipeline):
     """The fast training path around the same kernels: fused MSE + metrics, flat Adam, and the whole
     step (fwd + loss + bwd + [grad all-reduce] + Adam) optionally replayed from a CUDA graph.
 
@@ -598,19 +663,20 @@ class FusedTrainer:
         sx, st_ = self._static
         return self._replay() if self.use_graph else self._step_impl(sx, st_)
 
+    def _host_static(self, shape):
+        self._prepare(shape, next(self.net.parameters()).device)
+        return self._static
+
     def step_host(self, hx: torch.Tensor, ht: torch.Tensor) -> torch.Tensor:
-        """one training step from (pinned) HOST tensors: async H2D of the batch into the static device buffers,
-        then the step; returns the device loss tensor (the caller's .item() is the D2H read)."""
-        dev = next(self.net.parameters()).device
-        self._prepare(hx.shape, dev)
+        """one training step from (pinned) HOST tensors: async H2D of the batch into the static device buffers (or the
+        copy prefetch_host() staged for these tensors), then the step; returns the device loss tensor (the caller's
+        .item() -- or read_async() -- is the D2H read)."""
         self._set_synth(None)
-        sx, st_ = self._static
-        sx.copy_(hx, non_blocking=True)
-        st_.copy_(ht, non_blocking=True)
+        sx, st_ = self._load_host_batch(hx, ht)
         return (self._replay() if self.use_graph else self._step_impl(sx, st_))[0]
 
 
-class FineTuneTrainer:
+class FineTuneTrainer(_HostPipeline):
     """The fast path of the 12-lead fine-tuning step (Transfer_learning.py:71-82 driving denoise_train.py:51-57):
     `newrale` = Conv1d(12->6,k13) -> Conv1d(6->2,k13) -> frozen RA-LENet core -> Conv1d(2->6,k13) -> Conv1d(6->12,k13)
     (model/ralenet_12leads.py:680-709), MSE, Adam(lr 1e-3) on the 2,210 parameters of the four convolutions.
@@ -743,12 +809,14 @@ class FineTuneTrainer:
         self._t.copy_(target, non_blocking=True)
         return self._run()
 
+    def _host_static(self, shape):
+        self._prepare(shape, self.convs[0].weight.device)
+        return self._x, self._t
+
     def step_host(self, hx: torch.Tensor, ht: torch.Tensor) -> torch.Tensor:
-        """the same from pinned HOST tensors (async H2D inside); returns the device loss tensor."""
-        dev = self.convs[0].weight.device
-        self._prepare(hx.shape, dev)
-        self._x.copy_(hx, non_blocking=True)
-        self._t.copy_(ht, non_blocking=True)
+        """the same from pinned HOST tensors (async H2D inside, or the copy prefetch_host() staged for these tensors);
+        returns the device loss tensor."""
+        self._load_host_batch(hx, ht)
         return self._run()[0]
 
     def close(self):

@@ -759,6 +759,40 @@ def test_fused_trainer_step_synth(graph):
         assert float((p.detach() - q.detach()).abs().max()) <= 3.2e-3, n
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_trainer_step_host_with_prefetch(graph):
+    """FusedTrainer.prefetch_host / step_host: the batch staged on the copy stream one step ahead is the batch the step
+    trains on (and a step_host without a matching prefetch copies from the host itself); equals step() on the same
+    batches."""
+    from ecg_denoise_b200.engine import FusedTrainer
+    from ecg_denoise_b200.model import transformer
+    from oracle import synth_weights as SW
+    sd = SW.make_state_dict("rw", 1, 9)
+    B, NB = 16, 3
+    g = torch.Generator().manual_seed(5)
+    hx = [torch.randn(B, 2, 256, generator=g).pin_memory() for _ in range(NB)]
+    ht = [torch.randn(B, 2, 256, generator=g).pin_memory() for _ in range(NB)]
+
+    def fresh():
+        m = transformer.ralenet(high_level_enhence=True)
+        m.load_state_dict(sd)
+        return m.cuda()
+
+    ma, mb = fresh(), fresh()
+    ta, tb = FusedTrainer(ma, use_graph=graph), FusedTrainer(mb, use_graph=False)
+    ta.prefetch_host(hx[0], ht[0])
+    for it in range(5):
+        i = it % NB
+        la_dev = ta.step_host(hx[i], ht[i])
+        assert ta._staged_key is None                      # the staged copy (or, at it == 3, the host copy) was consumed
+        if it != 2:                                        # step 3 runs without a prefetch: direct host copy
+            ta.prefetch_host(hx[(it + 1) % NB], ht[(it + 1) % NB])
+        la = la_dev.item()
+        lb = tb.step(hx[i].cuda(), ht[i].cuda())[0].item()
+        assert abs(la - lb) <= 1e-5 * abs(lb), (it, la, lb)
+    _cmp(f"step_host_prefetch/graph{int(graph)}/flat_grad", ma._plan.flat_grad, mb._plan.flat_grad, RTOL)
+
+
 @pytest.mark.parametrize("stage", [2, 3, 4])
 @pytest.mark.parametrize("B", [1, 5, 37])
 def test_wgrad_register_tile_kernel_vs_oracle(ops, stage, B):

@@ -165,12 +165,13 @@ def reference_model(sd):
     return m, R
 
 
-def reference_train_loop(model, x, t, lr=1e-3):
+def reference_train_loop(model, x, t, lr=1e-3, opt=None):
     """denoise_train.py:24, 51-57 verbatim in behaviour: Adam(lr 1e-3); zero_grad, model(data), F.mse_loss,
-    loss.item(), backward, step."""
+    loss.item(), backward, step.  (`opt`: another optimizer object for the same loop.)"""
     import torch
     import torch.nn.functional as F
-    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    if opt is None:
+        opt = torch.optim.Adam(model.parameters(), lr=lr)
     model.train()
 
     def step():
@@ -589,10 +590,29 @@ def dropin_record(dev, sd, B, steps, warmup):
     e1.record()
     torch.cuda.synchronize()
     ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+    own = _lib.launch_count(reset=True) // steps
+    # the same loop with ONE line changed: the optimizer is ecg_denoise_b200.optim.Adam (one kernel over the flat
+    # parameter buffer instead of torch's foreach pass over ~300 tensors)
+    from ecg_denoise_b200 import optim as rl_optim
+    m2 = transformer.ralenet(high_level_enhence=True)
+    m2.load_state_dict(sd)
+    m2 = m2.to(dev)
+    step2 = reference_train_loop(m2, x, t, opt=rl_optim.Adam(m2, lr=1e-3))
+    for _ in range(warmup):
+        step2()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss2 = step2()
+    torch.cuda.synchronize()
+    ms2 = 1e3 * (time.perf_counter() - t0)
     return {"value": B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
-            "final_loss": float(loss), "own_launches_per_step": _lib.launch_count(reset=True) // steps,
+            "final_loss": float(loss), "own_launches_per_step": own,
             "what": f"denoise_train.py:51-57 loop on ecg_denoise_b200.model.transformer.ralenet: zero_grad, model(data), "
-                    f"F.mse_loss, loss.item(), backward, torch.optim.Adam.step; {B} x 2 x 256 windows"}
+                    f"F.mse_loss, loss.item(), backward, torch.optim.Adam.step; {B} x 2 x 256 windows",
+            "flat_adam": {"value": B * steps / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / steps,
+                          "final_loss": float(loss2),
+                          "what": "the same loop, optimizer line changed to ecg_denoise_b200.optim.Adam(model, lr=1e-3)"}}
 
 
 def timed_train(trainer, dx, dt, steps, warmup, barrier):

@@ -50,15 +50,15 @@ class NetPlan:
 
     # -- flattening ------------------------------------------------------------------------------
     def _aliased(self) -> bool:
+        """every Parameter slot of the network still holds the Parameter object the plan knows, and its storage is
+        still its slice of the flat buffer.  Runs before every forward and backward, so it goes through the cached
+        (module, name) slots -- ~300 dict lookups and integer compares, 0.1 ms -- instead of walking the module tree
+        (net.parameters() costs 1.5 ms per call for the 311 parameters: a third of the drop-in step at 256 windows)."""
         if self.flat is None or not self.params:
             return False
         base = self.flat.data_ptr()
-        ps = list(self.net.parameters())
-        if len(ps) != len(self.params):
-            return False
-        dev = self.flat.device
-        for p, q, o in zip(ps, self.params, self.offsets):      # ~300 integer compares
-            if p is not q or p.data_ptr() != base + 4 * o or p.device != dev:
+        for (mod, name), q, o in zip(self._slots, self.params, self.offsets):
+            if mod._parameters.get(name) is not q or q.data_ptr() != base + 4 * o:
                 return False
         return True
 
@@ -89,6 +89,15 @@ class NetPlan:
                     p.grad = flat_grad[o:o + p.numel()].view(p.shape)
         self.flat, self.flat_grad, self.params, self.offsets = flat, flat_grad, ps, offs
         self.n_flat = n
+        # where each Parameter lives (same order as net.parameters(): named_parameters walks named_modules and
+        # de-duplicates shared Parameters the same way)
+        slot_of = {}
+        for mod in self.net.modules():
+            for name, q in mod._parameters.items():
+                if q is not None and id(q) not in slot_of:
+                    slot_of[id(q)] = (mod, name)
+        self._slots = [slot_of[id(q)] for q in ps]
+        self._grad_views = None
         self.bn_stats = torch.zeros(64, device=device, dtype=torch.float32)
         self._build_tables()
 
@@ -105,6 +114,7 @@ class NetPlan:
                 if p.grad is not None and p.grad.data_ptr() == old_base + 4 * o:
                     p.grad = buf[o:o + p.numel()].view(p.shape)
         self.flat_grad = buf
+        self._grad_views = None
         self._build_tables()
 
     def _ptr_of(self, p: Optional[torch.Tensor], grad: bool):
@@ -199,14 +209,18 @@ class NetPlan:
         if not todo:
             return False
         fresh = True
+        if self._grad_views is None:        # the views are built once (slicing 311 tensors per step costs ~1 ms)
+            self._grad_views = {id(p): self.flat_grad[o:o + p.numel()].view(p.shape)
+                                for p, o in zip(self.params, self.offsets)}
+        views = self._grad_views
         n_train = sum(1 for p in self.params if p.requires_grad)
         if len(todo) == n_train and all(g is None for _, _, g in todo):
             self.flat_grad.zero_()          # the standard case after zero_grad(set_to_none=True): one memset
             for p, o, _ in todo:
-                p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+                p.grad = views[id(p)]
             return fresh
         for p, o, g in todo:
-            view = self.flat_grad[o:o + p.numel()].view(p.shape)
+            view = views[id(p)]
             if g is None:
                 view.zero_()
             else:

@@ -203,7 +203,6 @@ __global__ void __launch_bounds__(RL_NT) stem_bwd_apply_kernel(const rl_stem_bwd
   __shared__ float sx[2 * (MAXL + 2)];
   __shared__ float sdc[8 * (MAXL + 2)];
   __shared__ float sw[48], sb[8], smu[8], srs[8], sgam[8], sm1[8], sm2[8];
-  __shared__ float sgrad[56];
   const int L = a.L, tid = threadIdx.x;
   load_stem_window(sx, sw, sb, a.x + (size_t)blockIdx.x * 2 * L, a.conv_w, a.conv_b, L);
   if (tid < 8) {
@@ -223,21 +222,14 @@ __global__ void __launch_bounds__(RL_NT) stem_bwd_apply_kernel(const rl_stem_bwd
       sm2[tid] = 0.f;
     }
   }
-  if (tid < 56) sgrad[tid] = 0.f;
   for (int i = tid; i < 8 * (L + 2); i += RL_NT) sdc[i] = 0.f;
   __syncthreads();
   const float* gw = a.g + (size_t)blockIdx.x * L * 8;
   const float* g2w = a.g2 ? a.g2 + (size_t)blockIdx.x * L * 8 : nullptr;
-  float gwacc[48], gbacc[8];
-#pragma unroll
-  for (int i = 0; i < 48; ++i) gwacc[i] = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) gbacc[i] = 0.f;
   const bool train = a.training;
   for (int t = tid; t < L; t += RL_NT) {
     float c[8];
     stem_conv(sx, L, t, sw, sb, c);
-    const float xs[6] = {sx[t], sx[t + 1], sx[t + 2], sx[L + 2 + t], sx[L + 2 + t + 1], sx[L + 2 + t + 2]};
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
       float g = __ldg(gw + t * 8 + o);
@@ -247,27 +239,32 @@ __global__ void __launch_bounds__(RL_NT) stem_bwd_apply_kernel(const rl_stem_bwd
       const float da = train ? srs[o] * (dah - sm1[o] - ah * sm2[o]) : dah * srs[o];
       const float dc = da * (c[o] > 0.f ? 1.f : 0.2f);
       sdc[o * (L + 2) + t + 1] = dc;
-      gbacc[o] += dc;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) gwacc[o * 6 + k] = fmaf(dc, xs[k], gwacc[o * 6 + k]);
-    }
-  }
-  if (a.d_conv_w) {
-#pragma unroll
-    for (int i = 0; i < 48; ++i) {
-      const float r = warp_sum(gwacc[i]);
-      if ((tid & 31) == 0) atomicAdd(&sgrad[i], r);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float r = warp_sum(gbacc[i]);
-      if ((tid & 31) == 0) atomicAdd(&sgrad[48 + i], r);
     }
   }
   __syncthreads();
   if (a.d_conv_w) {
-    if (tid < 48) atomicAdd(a.d_conv_w + tid, sgrad[tid]);
-    else if (tid < 56) atomicAdd(a.d_conv_b + tid - 48, sgrad[tid]);
+    // dW[o][i][k] = sum_t dc[o][t] x[i][t+k-1], db[o] = sum_t dc[o][t], from the two shared-memory tiles: thread =
+    // (one of the 56 sums, one of 8 token segments), the 8 segments of a sum sit in neighbouring lanes (3 shuffles),
+    // one red.global per sum and CTA.  (Round 2 kept 56 partial sums per token thread and pushed each through a
+    // 5-step warp reduction plus a shared-memory atomic: 60 % of the samples of head_bwd, ncu r2_v38.)
+    const int seg = tid & 7;                               // tokens seg, seg + 8, ...: neighbouring lanes, neighbouring words
+    for (int jb = 0; jb < 56; jb += RL_NT >> 3) {          // (same trip count for every thread: full-warp shuffles)
+      const int j = jb + (tid >> 3);
+      float acc = 0.f;
+      if (j < 48) {
+        const int o = j / 6, i = (j % 6) / 3, k = j % 3;
+        const float* pd = sdc + o * (L + 2) + 1;
+        const float* px = sx + i * (L + 2) + k;
+        for (int t = seg; t < L; t += 8) acc = fmaf(pd[t], px[t], acc);
+      } else if (j < 56) {
+        const float* pd = sdc + (j - 48) * (L + 2) + 1;
+        for (int t = seg; t < L; t += 8) acc += pd[t];
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (seg == 0 && j < 56) atomicAdd(j < 48 ? a.d_conv_w + j : a.d_conv_b + j - 48, acc);
+    }
   }
   if (a.dx) {   // dx[i][t] = sum_{o,k} dc[o][t-k+1] w[o][i][k]
     float* dxw = a.dx + (size_t)blockIdx.x * 2 * L;
@@ -322,7 +319,6 @@ __global__ void __launch_bounds__(RL_NT) head_bwd_kernel(const rl_head_bwd_args 
   __shared__ float ss[(MAXL + 2) * 8];
   __shared__ float sdo[2 * (MAXL + 2)];
   __shared__ float sw[48];
-  __shared__ float sgrad[50];
   const int L = a.L, tid = threadIdx.x;
   const float* xw = a.x + (size_t)blockIdx.x * L * 8;
   const float* kw = a.skip ? a.skip + (size_t)blockIdx.x * L * 8 : nullptr;
@@ -341,7 +337,6 @@ __global__ void __launch_bounds__(RL_NT) head_bwd_kernel(const rl_head_bwd_args 
     sdo[i] = (p >= 0 && p < L) ? __ldg(dw + o * L + p) : 0.f;
   }
   if (tid < 48) sw[tid] = __ldg(a.w + tid);
-  if (tid < 50) sgrad[tid] = 0.f;
   __syncthreads();
   // ds[t][i] = sum_{o,k} dout[o][t-k+1] w[o][i][k]
   float* dsw = a.ds + (size_t)blockIdx.x * L * 8;
@@ -354,38 +349,27 @@ __global__ void __launch_bounds__(RL_NT) head_bwd_kernel(const rl_head_bwd_args 
       for (int k = 0; k < 3; ++k) s = fmaf(sdo[o * (L + 2) + (t - k + 1) + 1], sw[o * 24 + i * 3 + k], s);
     dsw[idx] = s;
   }
-  if (a.d_w) {  // dW[o][i][k] = sum_t dout[o][t] s[t+k-1][i];  thread per (o,i,k) pair x token slice
-    float acc[48];
-#pragma unroll
-    for (int i = 0; i < 48; ++i) acc[i] = 0.f;
-    float b0 = 0.f, b1 = 0.f;
-    for (int t = tid; t < L; t += RL_NT) {
-      const float d0 = sdo[t + 1], d1 = sdo[(L + 2) + t + 1];
-      b0 += d0;
-      b1 += d1;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float sv = ss[(t + k) * 8 + i];
-          acc[i * 3 + k] = fmaf(d0, sv, acc[i * 3 + k]);
-          acc[24 + i * 3 + k] = fmaf(d1, sv, acc[24 + i * 3 + k]);
-        }
+  if (a.d_w) {
+    // dW[o][i][k] = sum_t dout[o][t] s[t+k-1][i], db[o] = sum_t dout[o][t]: thread = (one of the 50 sums, one of 8
+    // token segments); 3 shuffles join the segments, one red.global per sum and CTA (see stem_bwd_apply_kernel)
+    const int seg = tid & 7;                               // tokens seg, seg + 8, ...
+    for (int jb = 0; jb < 50; jb += RL_NT >> 3) {          // (same trip count for every thread: full-warp shuffles)
+      const int j = jb + (tid >> 3);
+      float acc = 0.f;
+      if (j < 48) {
+        const int o = j / 24, i = (j % 24) / 3, k = j % 3;
+        const float* pd = sdo + o * (L + 2) + 1;
+        const float* ps = ss + k * 8 + i;
+        for (int t = seg; t < L; t += 8) acc = fmaf(pd[t], ps[t * 8], acc);
+      } else if (j < 50) {
+        const float* pd = sdo + (j - 48) * (L + 2) + 1;
+        for (int t = seg; t < L; t += 8) acc += pd[t];
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (seg == 0 && j < 50) atomicAdd(j < 48 ? a.d_w + j : a.d_b + j - 48, acc);
     }
-#pragma unroll
-    for (int i = 0; i < 48; ++i) {
-      const float r = warp_sum(acc[i]);
-      if ((tid & 31) == 0) atomicAdd(&sgrad[i], r);
-    }
-    b0 = warp_sum(b0);
-    b1 = warp_sum(b1);
-    if ((tid & 31) == 0) {
-      atomicAdd(&sgrad[48], b0);
-      atomicAdd(&sgrad[49], b1);
-    }
-    __syncthreads();
-    if (tid < 48) atomicAdd(a.d_w + tid, sgrad[tid]);
-    else if (tid < 50) atomicAdd(a.d_b + tid - 48, sgrad[tid]);
   }
 }
 

@@ -96,13 +96,16 @@ __device__ __forceinline__ void attn_fwd_body(const rl_attn_fwd_args& a, float* 
     WS::Proj::prefetch(sw, a.wp, C, nullptr, C);              // lands while the attention core runs
     const float* bq = a.bq;
     const float* bkv = a.bkv;
-    acc.epilogue([&](int t, int n, float v) {
-      if (n < C) {
-        sq[t * LDC + n] = v + (bq ? __ldg(bq + n) : 0.f);
-      } else {
-        v += bkv ? __ldg(bkv + n - C) : 0.f;
-        if (n < 2 * C) sk[t * LDC + n - C] = v; else sv[t * LDC + n - 2 * C] = v;
+    acc.epilogue_pairs([&](int t, int n, float v0, float v1) {   // two adjacent columns: 8-byte bias loads and stores
+      const int seg = n / C, c = n - seg * C;                    // q | k | v (a pair never straddles: C is even)
+      const float* bsrc = (seg == 0) ? bq : bkv;
+      if (bsrc) {
+        const float2 b2 = __ldg(reinterpret_cast<const float2*>(bsrc + (seg == 2 ? C : 0) + c));
+        v0 += b2.x;
+        v1 += b2.y;
       }
+      float* dst = (seg == 0) ? sq : (seg == 1) ? sk : sv;
+      *reinterpret_cast<float2*>(dst + t * LDC + c) = make_float2(v0, v1);
     });
   }
   __syncthreads();
@@ -137,9 +140,13 @@ __device__ __forceinline__ void attn_fwd_body(const rl_attn_fwd_args& a, float* 
     RL_TS(attn, 7);
     const float* bp = a.bp;
     float* yw = a.y + woff;
-    acc.epilogue2(rv, [&](int t, int n, float v, float add) {
-      v += bp ? __ldg(bp + n) : 0.f;
-      yw[t * C + n] = v + add;
+    acc.epilogue2_pairs(rv, [&](int t, int n, float v0, float v1, float add0, float add1) {
+      if (bp) {
+        const float2 b2 = __ldg(reinterpret_cast<const float2*>(bp + n));
+        v0 += b2.x;
+        v1 += b2.y;
+      }
+      *reinterpret_cast<float2*>(yw + t * C + n) = make_float2(v0 + add0, v1 + add1);
     });
   }
   RL_TS(attn, 8);
@@ -240,9 +247,9 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
     // max |do| of the window is taken from the accumulators on their way to shared memory (one barrier and one pass
     // over the tile less than reading it back)
     float am = 0.f;
-    acc.epilogue([&](int t, int n, float v) {
-      sdo[t * LDC + n] = v;
-      am = fmaxf(am, fabsf(v));
+    acc.epilogue_pairs([&](int t, int n, float v0, float v1) {
+      *reinterpret_cast<float2*>(sdo + t * LDC + n) = make_float2(v0, v1);
+      am = fmaxf(am, fmaxf(fabsf(v0), fabsf(v1)));
     });
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
@@ -317,7 +324,9 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) attn_bwd_kernel(const rl_attn_
     MmaTile<L, C> acc;
     acc.init();
     AttnW<C>::Dgrad::template run<true>(acc, sdq, LDC, sw, a.wq, C, a.wkv, C, C, LP);
-    acc.epilogue([&](int t, int n, float v) { su[t * LDC + n] = v; });
+    acc.epilogue_pairs([&](int t, int n, float v0, float v1) {
+      *reinterpret_cast<float2*>(su + t * LDC + n) = make_float2(v0, v1);
+    });
   }
   __syncthreads();
 

@@ -223,7 +223,9 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) ffn_bwd_kernel(const rl_ffn_bw
     MmaTile<L, C> acc;
     acc.init();
     WStream<C, HC, B_KN>::template run<true>(acc, sd, LDH, sw, a.w1, 1 << 30, nullptr, C);
-    acc.epilogue([&](int t, int n, float v) { su[t * LDC + n] = v; });
+    acc.epilogue_pairs([&](int t, int n, float v0, float v1) {
+      *reinterpret_cast<float2*>(su + t * LDC + n) = make_float2(v0, v1);
+    });
   }
   __syncthreads();
 

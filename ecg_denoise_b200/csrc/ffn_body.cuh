@@ -58,11 +58,20 @@ __device__ __forceinline__ void ffn_fwd_body(const rl_ffn_fwd_args& a, float* sm
     WStream<C, HC, B_NK>::prefetch(sw, a.w2, C, nullptr, HC);      // lands behind the GELU / local-enhancement phase
     const float* b1 = a.b1;
     float* hs = a.h ? a.h + (size_t)blockIdx.x * L * HC : nullptr;
+    const bool partial = (a.le_mode == RL_LE_PARTIAL);
     acc.epilogue_pairs([&](int t, int n, float v0, float v1) {      // two hidden units per call: packed-fp32 GELU
       if (b1) { v0 += __ldg(b1 + n); v1 += __ldg(b1 + n + 1); }
       if (hs) *reinterpret_cast<float2*>(hs + t * HC + n) = make_float2(v0, v1);
       float g0, g1;
       gelu2(v0, v1, g0, g1);
+      if (partial) {
+        // partial local enhancement: only hidden unit 0 is convolved, every other unit goes straight through the
+        // second GELU here, in registers (round 2 made a second pass over the whole L x 4C tile in shared memory)
+        float q0, q1;
+        gelu2(g0, g1, q0, q1);
+        g1 = q1;
+        if (n != 0) g0 = q0;                                        // unit 0 keeps GELU(h): FIR + GELU below
+      }
       *reinterpret_cast<float2*>(sh + t * LDH + n) = make_float2(g0, g1);
     });
   }
@@ -77,13 +86,7 @@ __device__ __forceinline__ void ffn_fwd_body(const rl_ffn_fwd_args& a, float* sm
       sfir[t] = w0 * p + w1 * sh[t * LDH] + w2 * n;
     }
     __syncthreads();
-    for (int i = tid; i < L * HC / 2; i += RL_NT) {        // two hidden units at a time on the packed fp32 pipe
-      const int t = (2 * i) / HC, n = (2 * i) % HC;
-      float2 f = *reinterpret_cast<const float2*>(sh + t * LDH + n);
-      if (n == 0) f.x = sfir[t];
-      gelu2(f.x, f.y, f.x, f.y);
-      *reinterpret_cast<float2*>(sh + t * LDH + n) = f;
-    }
+    for (int t = tid; t < L; t += RL_NT) sh[t * LDH] = gelu_f(sfir[t]);
     __syncthreads();
   } else if (a.le_mode == RL_LE_DEPTHWISE) {
     for (int c = tid; c < HC; c += RL_NT) {
@@ -121,9 +124,13 @@ __device__ __forceinline__ void ffn_fwd_body(const rl_ffn_fwd_args& a, float* sm
 #pragma unroll
           for (int e = 0; e < 4; ++e) rv[r][c][e] += ev[r][c][e];
     }
-    acc.epilogue2(rv, [&](int t, int n, float v, float add) {
-      v += b2 ? __ldg(b2 + n) : 0.f;
-      yw[t * C + n] = v + add;
+    acc.epilogue2_pairs(rv, [&](int t, int n, float v0, float v1, float add0, float add1) {
+      if (b2) {
+        const float2 bb = __ldg(reinterpret_cast<const float2*>(b2 + n));
+        v0 += bb.x;
+        v1 += bb.y;
+      }
+      *reinterpret_cast<float2*>(yw + t * C + n) = make_float2(v0 + add0, v1 + add1);
     });
   }
 }

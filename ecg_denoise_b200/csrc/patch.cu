@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_fwd_kernel(const rl_patc
   float* yw = a.y + woff;
   float skv[MmaTile<rows, CN>::RT][MmaTile<rows, CN>::CT][4] = {};
   if (sk) acc.gather(sk, CN, skv);                 // one batch of loads, not one round trip per element
-  acc.epilogue2(skv, [&](int r, int n, float v, float s) { yw[r * CN + n] = v + s; });
+  acc.epilogue2_pairs(skv, [&](int r, int n, float v0, float v1, float s0, float s1) {
+    *reinterpret_cast<float2*>(yw + r * CN + n) = make_float2(v0 + s0, v1 + s1);
+  });
 }
 
 template <int CN, int WIN>
@@ -94,7 +96,9 @@ __global__ void __launch_bounds__(RL_NT, RL_MINB) patch_bwd_kernel(const rl_patc
     MmaTile<rows, CN> acc;
     acc.init();
     WStream<CN, CN, B_KN>::template run<true>(acc, sg, LDA, sw, a.w, 1 << 30, nullptr, CN);
-    acc.epilogue([&](int r, int n, float v) { su[r * LDA + n] = v; });
+    acc.epilogue_pairs([&](int r, int n, float v0, float v1) {
+      *reinterpret_cast<float2*>(su + r * LDA + n) = make_float2(v0, v1);
+    });
   }
   __syncthreads();
   float* dxw = a.dx + woff;

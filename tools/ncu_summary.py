@@ -1,6 +1,7 @@
 """Summarise an `ncu --page raw --csv` export: python tools/ncu_summary.py raw.csv out_summary.csv [traffic.json]
 Keeps the columns the judge reads; optionally records dram read+write bytes per launch per kernel label
-(bench.py's roofline.traffic reads that file)."""
+(bench.py's roofline.traffic reads that file; `source` names the summary csv, which is the file committed under
+profiles/)."""
 import csv, json, re, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, data = rows[0], rows[2:]
@@ -34,7 +35,7 @@ if len(sys.argv) > 3:
         name = name.replace("_umma_kernel", "_umma")
         label = f"{name}<{tags[0]}>"
         b = float(r[ir]) * SCALE[units[ir]] + float(r[iw]) * SCALE[units[iw]]
-        e = tr.setdefault(label, {"bytes": [], "source": sys.argv[1].split("/")[-1]})
+        e = tr.setdefault(label, {"bytes": [], "source": sys.argv[2].split("/")[-1]})
         e["bytes"].append(b)
     for e in tr.values():
         if "bytes" in e and isinstance(e["bytes"], list):

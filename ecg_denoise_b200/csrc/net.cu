@@ -100,7 +100,10 @@ int side_ctx(SideCtx** out) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (!g_side.ready || g_side.dev != dev) {
-    cudaError_t e = cudaStreamCreateWithFlags(&g_side.side, cudaStreamNonBlocking);
+    // RALENET_SIDE_PRIO (A/B switch): priority of the weight-gradient stream (0 = lowest = default; negative = higher).
+    // Kernel nodes captured into a CUDA graph inherit the priority of the stream they were captured on.
+    const char* pe = getenv("RALENET_SIDE_PRIO");
+    cudaError_t e = cudaStreamCreateWithPriority(&g_side.side, cudaStreamNonBlocking, pe ? atoi(pe) : 0);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) {
       e = cudaEventCreateWithFlags(&g_side.ev_main[i], cudaEventDisableTiming);
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_side.ev_side[i], cudaEventDisableTiming);

@@ -245,6 +245,27 @@ class NetPlan:
         return c
 
 
+# Per-GPU batches up to this many windows capture the training step on a HIGH-priority stream (see _capture_stream).
+PRIO_MAX_BATCH = 512
+
+
+def _capture_stream(batch: int):
+    """stream the step graph is captured on.  Kernel nodes inherit the launch priority of their capture stream, and
+    net.cu forks the weight-gradient GEMMs of the backward pass to a stream of the lowest priority.  While a launch of
+    the data-gradient chain is at most about two waves of CTAs (one window per CTA, 296 slots), ranking the chain above
+    that branch lets its CTAs take freed SM slots first and the weight-gradient CTAs fill what is left: measured on one
+    B200 (profiles/r2_v50_exp_prio*.txt) 1.910 -> 1.778 ms per step at 256 windows, 3.400 -> 3.313 ms at 512.  With more
+    waves the same ranking starves the branch until the chain has to wait for it (1024 windows: 6.06 -> 6.10 ms,
+    2048: 11.47 -> 11.96, 4096: 22.41 -> 23.19), so larger batches keep equal priorities (PRIO_MAX_BATCH).
+    RALENET_MAIN_PRIO overrides (0 = lowest = torch's default, negative = higher)."""
+    env = os.environ.get("RALENET_MAIN_PRIO")
+    if env is not None and env != "":
+        return torch.cuda.Stream(priority=int(env))
+    if batch <= PRIO_MAX_BATCH:
+        return torch.cuda.Stream(priority=torch.cuda.Stream.priority_range()[1])
+    return None
+
+
 def workspace_bytes(B: int, L0: int, save: bool) -> int:
     return int(_lib.load().ralenet_net_workspace_bytes(B, L0, int(save)))
 
@@ -614,7 +635,7 @@ class FusedTrainer(_HostPipeline):
                 # no launch gap between the segments); falls back to the segmented form if capture is refused
                 try:
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    with torch.cuda.graph(g, stream=_capture_stream(sx.shape[0]), capture_error_mode="thread_local"):
                         for _, fn in self._pieces(sx, st_):
                             fn()
                     plan = [(g, None)]
@@ -631,7 +652,8 @@ class FusedTrainer(_HostPipeline):
                         plan.append((None, fn))
                         continue
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
+                    with torch.cuda.graph(g, pool=pool, stream=_capture_stream(sx.shape[0]),
+                                          capture_error_mode="thread_local"):
                         fn()
                     pool = g.pool()
                     plan.append((g, None))

@@ -246,17 +246,18 @@ class NetPlan:
 
 
 # Per-GPU batches up to this many windows capture the training step on a HIGH-priority stream (see _capture_stream).
-PRIO_MAX_BATCH = 512
+PRIO_MAX_BATCH = 768
 
 
 def _capture_stream(batch: int):
     """stream the step graph is captured on.  Kernel nodes inherit the launch priority of their capture stream, and
     net.cu forks the weight-gradient GEMMs of the backward pass to a stream of the lowest priority.  While a launch of
-    the data-gradient chain is at most about two waves of CTAs (one window per CTA, 296 slots), ranking the chain above
+    the data-gradient chain is at most two or three waves of CTAs (one window per CTA, 296 slots), ranking the chain above
     that branch lets its CTAs take freed SM slots first and the weight-gradient CTAs fill what is left: measured on one
-    B200 (profiles/r2_v50_exp_prio*.txt) 1.910 -> 1.778 ms per step at 256 windows, 3.400 -> 3.313 ms at 512.  With more
-    waves the same ranking starves the branch until the chain has to wait for it (1024 windows: 6.06 -> 6.10 ms,
-    2048: 11.47 -> 11.96, 4096: 22.41 -> 23.19), so larger batches keep equal priorities (PRIO_MAX_BATCH).
+    B200 (profiles/r2_v50_exp_prio*.txt) 1.910 -> 1.778 ms per step at 256 windows, 2.927 -> 2.798 at 384, 3.400 -> 3.313
+    at 512, 4.887 -> 4.835 at 768.  With more waves the same ranking starves the branch until the chain has to wait for
+    it (1024 windows: 6.06 -> 6.10 ms, 2048: 11.47 -> 11.96, 4096: 22.41 -> 23.19), so larger batches keep equal
+    priorities (PRIO_MAX_BATCH).
     RALENET_MAIN_PRIO overrides (0 = lowest = torch's default, negative = higher)."""
     env = os.environ.get("RALENET_MAIN_PRIO")
     if env is not None and env != "":

@@ -2,9 +2,9 @@
 # experiment: launch priority of the data-gradient chain (capture stream, RALENET_MAIN_PRIO) against the forked
 # weight-gradient branch (RALENET_SIDE_PRIO) inside the step graph.
 # usage (through gpurun): bash tools/exp_prio.sh TAG            256 windows (twice, interleaved) and 4096 windows
-#                         bash tools/exp_prio.sh TAG sweep      512 / 1024 / 2048 windows, base against main-hi
+#                         bash tools/exp_prio.sh TAG sweep ["B ..."]   512 / 1024 / 2048 windows (or the given batch sizes), base against main-hi
 tag=${1:-prio}
-o=gpurun_out/${tag}_exp_prio${2:+_$2}.txt
+o=gpurun_out/${tag}_exp_prio${2:+_$2}${3:+2}.txt
 : > $o
 B="--no-cpu-baseline --no-extras --no-profile"
 run() {  # name, env...
@@ -13,7 +13,7 @@ run() {  # name, env...
 }
 python -c "import torch; print(torch.cuda.Stream.priority_range())" | tee -a $o
 if [ "$2" = sweep ]; then
-  for b in 512 1024 2048; do
+  for b in ${3:-512 1024 2048}; do
     EXTRA="--batch $b --steps 20 --warmup 4"
     run base RALENET_MAIN_PRIO=0
     run main-hi RALENET_MAIN_PRIO=-3

@@ -315,3 +315,32 @@ def test_flat_parameter_plan_tracks_every_parameter_and_partial_grads():
     assert float((b.grad - 5.0).abs().max()) == 0.0
     assert float((c.grad - 1.0).abs().max()) == 0.0     # untouched slice kept its accumulated value
     assert a.grad.data_ptr() == plan.flat_grad.data_ptr() + 4 * plan.offsets[3]
+
+
+def test_step_graph_capture_priority_rule(monkeypatch):
+    """engine._capture_stream: per-GPU batches up to PRIO_MAX_BATCH capture the step on the highest-priority stream
+    (the data-gradient chain ranks above the forked weight-gradient branch), larger ones on torch's default capture
+    stream; RALENET_MAIN_PRIO overrides both ways (profiles/r2_v50_exp_prio*.txt is the measurement behind the rule)."""
+    from ecg_denoise_b200 import engine
+
+    made = []
+
+    class FakeStream:
+        def __init__(self, priority=0):
+            made.append(priority)
+
+        @staticmethod
+        def priority_range():
+            return (0, -3)
+
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.delenv("RALENET_MAIN_PRIO", raising=False)
+    assert isinstance(engine._capture_stream(256), FakeStream) and made == [-3]
+    assert isinstance(engine._capture_stream(engine.PRIO_MAX_BATCH), FakeStream) and made == [-3, -3]
+    assert engine._capture_stream(engine.PRIO_MAX_BATCH + 1) is None and engine._capture_stream(4096) is None
+    monkeypatch.setenv("RALENET_MAIN_PRIO", "0")
+    assert isinstance(engine._capture_stream(256), FakeStream) and made[-1] == 0
+    monkeypatch.setenv("RALENET_MAIN_PRIO", "-2")
+    assert isinstance(engine._capture_stream(4096), FakeStream) and made[-1] == -2
+    monkeypatch.setenv("RALENET_MAIN_PRIO", "")
+    assert engine._capture_stream(4096) is None
